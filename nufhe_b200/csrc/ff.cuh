@@ -1,0 +1,157 @@
+// ff.cuh -- arithmetic in Z_p, p = 2^64 - 2^32 + 1 (the field of nufhe's NTT transform,
+// reference: nufhe/transform/arithmetic.mako, nufhe/transform/ntt_cpu.py:23).
+//
+// All functions take and return CANONICAL representatives (< p) unless a name says otherwise.
+// The same source is compiled by nvcc for sm_100a and by g++ for the host-side lane emulation
+// (tests/ + csrc/host_emul.cpp), so the index/twiddle logic can be checked without a GPU.
+//
+// Identities used throughout (phi = 2^32):  phi^2 = phi - 1,  phi^3 = -1  (2^64 = 2^32 - 1, 2^96 = -1).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NB_HD __host__ __device__ __forceinline__
+#define NB_D __device__ __forceinline__
+#else
+#define NB_HD inline
+#define NB_D inline
+#endif
+
+namespace nb {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef int32_t i32;
+
+constexpr u64 FF_P = 0xffffffff00000001ULL;
+constexpr u64 FF_EPS = 0xffffffffULL;   // 2^64 mod p
+
+NB_HD u32 lo32(u64 x) { return (u32)x; }
+NB_HD u32 hi32(u64 x) { return (u32)(x >> 32); }
+NB_HD u64 pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+
+// x in [0, 2^64) -> canonical (arithmetic.mako:164-194 `mod`)
+NB_HD u64 ff_canon(u64 x) { return x >= FF_P ? x - FF_P : x; }
+
+// a - b mod p; a may be any 64-bit value, b canonical; result canonical iff a canonical.
+// (arithmetic.mako:122-161 `sub`): wrap-around of 2^64 is undone by subtracting 2^32-1.
+NB_HD u64 ff_sub(u64 a, u64 b)
+{
+#if defined(__CUDA_ARCH__)
+    u32 l, h, m;
+    asm("sub.cc.u32 %0, %3, %5;\n\t"
+        "subc.cc.u32 %1, %4, %6;\n\t"
+        "subc.u32 %2, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, %2;\n\t"
+        "subc.u32 %1, %1, 0;"
+        : "=&r"(l), "=&r"(h), "=&r"(m)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+    return pack(l, h);
+#else
+    u64 d = a - b;
+    return a < b ? d - FF_EPS : d;
+#endif
+}
+
+NB_HD u64 ff_neg(u64 a) { return a ? FF_P - a : 0; }
+
+// a + b mod p, both canonical (arithmetic.mako:78-119 `add`), computed as a - (p - b).
+NB_HD u64 ff_add(u64 a, u64 b) { return ff_sub(a, FF_P - b); }
+
+// v * (2^32 - 1) for a 32-bit v: always canonical ((2^32-1)^2 < p).
+NB_HD u64 ff_eps_mul(u32 v) { return ((u64)v << 32) - v; }
+
+// 128-bit (hi:lo) -> canonical  (arithmetic.mako:197-333 `mul`, reduction part :200-207)
+NB_HD u64 ff_reduce128(u64 lo, u64 hi)
+{
+    u64 t = ff_sub(lo, (u64)hi32(hi));             // - hi_hi * 2^96
+    // t is loose here (lo may be >= p); ff_eps_mul() is canonical, so one wrap fix is enough
+    u64 u = ff_eps_mul(lo32(hi));                  // + hi_lo * 2^64
+    u64 r = t + u;
+    if (r < u) r += FF_EPS;
+    return ff_canon(r);
+}
+
+NB_HD u64 ff_mul(u64 a, u64 b)
+{
+#if defined(__CUDA_ARCH__)
+    return ff_reduce128(a * b, __umul64hi(a, b));
+#else
+    unsigned __int128 pr = (unsigned __int128)a * b;
+    return ff_reduce128((u64)pr, (u64)(pr >> 64));
+#endif
+}
+
+// a*b + c*d mod p with a single reduction of the 129-bit sum
+NB_HD u64 ff_mul2_add(u64 a, u64 b, u64 c, u64 d)
+{
+    return ff_add(ff_mul(a, b), ff_mul(c, d));
+}
+
+// a * b * 2^-64 mod p, the reference's Montgomery product (arithmetic.mako:355-419 `mul_prepared`)
+constexpr u64 FF_RINV = 0xfffffffe00000001ULL;     // 2^-64 mod p (polynomial_transform_ntt.py:66)
+NB_HD u64 ff_mul_prepared(u64 a, u64 b) { return ff_mul(ff_mul(a, b), FF_RINV); }
+// a * 2^64 mod p (arithmetic.mako:336-352 `prepare_for_mul`)
+NB_HD u64 ff_prepare_for_mul(u64 a) { return ff_mul(a, FF_EPS); }
+
+// int32 -> field (ntt.mako:395-399) and field -> int32 (ntt.mako:402-408; ntt_cpu.py:74-80)
+NB_HD u64 ff_from_i32(i32 x) { return x >= 0 ? (u64)(u32)x : FF_P - (u64)(u32)(-(int64_t)x); }
+NB_HD i32 ff_to_i32(u64 v) { return (i32)(lo32(v) - (u32)(v > FF_P / 2)); }
+
+// ---- multiplication by 2^S (arithmetic.mako:465-1045 `lsh`, extended to any S mod 192) -------
+//
+// x << r (0 <= r < 32) as three 32-bit limbs y0 + y1*phi + y2*phi^2, then times phi^q with
+// phi^3 = -1; the three limbs land on {1, phi, phi^2} with signs and phi^2 is folded with phi - 1.
+// POS/NEG are canonical partial sums; the result is POS - NEG.
+struct Limbs3 { u32 y0, y1, y2; };
+
+NB_HD Limbs3 ff_bitshift(u64 x, int r)     // r in [0, 32)
+{
+    Limbs3 y;
+    u32 x0 = lo32(x), x1 = hi32(x);
+    if (r == 0) { y.y0 = x0; y.y1 = x1; y.y2 = 0; }
+    else {
+        y.y0 = x0 << r;
+        y.y1 = (x1 << r) | (x0 >> (32 - r));
+        y.y2 = x1 >> (32 - r);
+    }
+    return y;
+}
+
+// value = sign * (y0 + y1*phi + y2*phi^2) * phi^q, q in {0,1,2}, negate in {false,true}
+NB_HD u64 ff_limbs_combine(Limbs3 y, int q, bool negate)
+{
+    u64 pos, neg;
+    if (q == 0) {            // (y0 - y2) + (y1 + y2) phi
+        pos = ff_add(ff_canon(pack(y.y0, y.y1)), ff_eps_mul(y.y2));
+        neg = 0;
+    } else if (q == 1) {     // (-y2 - y1) + (y0 + y1) phi
+        pos = ff_add((u64)y.y0 << 32, ff_eps_mul(y.y1));
+        neg = y.y2;
+    } else {                 // (-y0 - y1) + (y0 - y2) phi
+        pos = ff_eps_mul(y.y0);
+        neg = ff_canon(pack(y.y1, y.y2));
+    }
+    return negate ? ff_sub(neg, pos) : ff_sub(pos, neg);
+}
+
+// x * 2^S mod p, S a compile-time constant (any non-negative integer; reduced mod 192)
+template <int S> NB_HD u64 ff_shl(u64 x)
+{
+    constexpr int s = S % 192;
+    constexpr int s96 = s % 96;
+    constexpr bool negate = s >= 96;
+    if (s == 0) return x;
+    if (s == 96) return ff_neg(x);
+    return ff_limbs_combine(ff_bitshift(x, s96 % 32), s96 / 32, negate);
+}
+
+// x * 2^s mod p for a run-time s in [0, 192)
+NB_HD u64 ff_shl_var(u64 x, int s)
+{
+    bool negate = s >= 96;
+    int s96 = negate ? s - 96 : s;
+    return ff_limbs_combine(ff_bitshift(x, s96 & 31), s96 >> 5, negate);
+}
+
+}  // namespace nb

@@ -1,0 +1,40 @@
+// tables.h -- host-side construction of the constant tables the kernels consume:
+//   * stage-T twiddles of the warp NTT (ntt_lane.cuh), forward and inverse, [slot][lane] order;
+//   * the permutation that takes a reference-format bootstrap-key row (natural NTT order,
+//     Montgomery form, nufhe/tlwe_gpu.py:199-236) to the lane-major plain form the MAC reads.
+// Host only (uses unsigned __int128); shared by the CUDA library and the host lane emulator.
+#pragma once
+#include <vector>
+#include "ntt_lane.cuh"
+
+namespace nb {
+
+inline u64 h_mul(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) % FF_P); }
+inline u64 h_pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = h_mul(r, a); a = h_mul(a, a); e >>= 1; } return r; }
+inline u64 h_inv(u64 a) { return h_pow(a, FF_P - 2); }
+
+constexpr u64 ROOT_GEN = 0xa70dc47e4cbdf43fULL;          // nufhe/transform/ntt_cpu.py:109
+
+struct NttTables {
+    std::vector<u64> fwd, inv;     // [slot * 32 + lane]
+    NttTables() : fwd(NTT_N), inv(NTT_N)
+    {
+        const u64 psi = h_pow(ROOT_GEN, (1ULL << 32) / 2048);
+        const u64 psi_inv = h_inv(psi), n_inv = h_inv(NTT_N);
+        for (int slot = 0; slot < SLOTS; slot++)
+            for (int lane = 0; lane < 32; lane++) {
+                int e = ntt_twiddle_exponent(lane, slot);
+                fwd[slot * 32 + lane] = h_pow(psi, e);
+                inv[slot * 32 + lane] = h_mul(h_pow(psi_inv, e), n_inv);
+            }
+    }
+};
+
+// Index into a reference BK row (2,2,2,1024) = [mi][j][mo][k] for element [mi][slot][j][lane][mo]
+// of the internal row layout (see kernels.cu: bk_prepare_kernel).
+inline size_t bk_internal_index(int mi, int slot, int j, int lane, int mo)
+{
+    return ((((size_t)mi * SLOTS + slot) * 2 + j) * 32 + lane) * 2 + mo;
+}
+
+}  // namespace nb

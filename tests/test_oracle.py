@@ -1,0 +1,135 @@
+"""The CPU oracle (oracle/nufhe_oracle.c) against the committed golden vectors, which were produced by
+the reference's own NumPy closures (tests/golden/make_golden.py).  CPU only."""
+import hashlib
+
+import numpy
+import pytest
+
+import gen_inputs as G
+from oracle import oracle as O
+
+
+def sha(arr):
+    return hashlib.sha256(numpy.ascontiguousarray(arr).tobytes()).hexdigest()
+
+
+def test_reduction_selftest():
+    assert O.selftest(seed=12345, n=200000) == 0
+
+
+def test_arithmetic(golden):
+    g = golden('arithmetic')
+    a, b, s = G.arithmetic_inputs()
+    assert (O.ff_mul(a, b) == g['mul']).all()
+    assert (O.ff_add(a, b) == g['add']).all()
+    assert (O.ff_sub(a, b) == g['sub']).all()
+    assert (O.ff_mul_prepared(a, b) == g['mul_prepared']).all()
+    assert (O.ff_prepare_for_mul(a) == g['prepare_for_mul']).all()
+    assert (O.ff_lsh(a, s) == g['lsh']).all()
+
+
+def test_ntt(golden):
+    g = golden('ntt')
+    x_i32, x_u64 = G.ntt_inputs()
+    assert (O.ntt_forward_i32(x_i32) == g['fwd_i32']).all()
+    assert (O.ntt_forward_u64(x_u64) == g['fwd_u64']).all()
+    assert (O.ntt_inverse_u64(x_u64) == g['inv_u64']).all()
+    assert (O.ntt_inverse_i32(x_u64) == g['inv_i32']).all()
+
+
+def test_ntt_roundtrip_and_convolution():
+    # same property as test/test_transform/test_computation.py:71-124 of the reference
+    rng = G.rs(7)
+    a = G.torus32(rng, (4, 1024))
+    b = G.torus32(rng, (4, 1024), -1000, 1000)
+    prod = O.ntt_inverse_i32(O.ff_mul(O.ntt_forward_i32(a), O.ntt_forward_i32(b)))
+    a64, b64 = a.astype(object), b.astype(object)
+    for q in range(4):
+        full = numpy.convolve(a64[q], b64[q])
+        neg = full[:1024].copy()
+        neg[:1023] -= full[1024:]
+        want = numpy.array([int(v) % 2**32 for v in neg], numpy.uint64).astype(numpy.uint32)
+        assert (prod[q].view(numpy.uint32) == want).all()
+    assert (O.ntt_inverse_i32(O.ntt_forward_i32(a)) == a).all()
+
+
+def test_small_kernels(golden):
+    g = golden('small')
+    assert (O.t32_to_phase(G.modswitch_inputs(), 2048) == g['phase']).all()
+    src, powers, bara = G.shift_inputs()
+    assert (O.shift_torus_polynomial(src, powers) == g['shift_plain']).all()
+    assert (O.shift_torus_polynomial(src, powers, invert_powers=True) == g['shift_inverted']).all()
+    assert (O.shift_torus_polynomial(src, bara, 3, minus_one=True) == g['shift_minus_one']).all()
+    ea, eb = O.tlwe_extract_lwe_samples(G.extract_inputs())
+    assert (ea == g['extract_a']).all() and (eb == g['extract_b']).all()
+    assert (O.tlwe_noiseless_trivial(src[:, 0, :]) == g['trivial']).all()
+    a, b = G.linear_inputs()
+    for name in ('nand', 'xor', 'andny'):
+        num, den, sa, sb = O.GATE_TABLE[name]
+        t_a, t_b = O.lwe_affine2(a, b, O.phase_to_t32(num, den), sa, sb)
+        assert (t_a == g['lin_%s_a' % name]).all() and (t_b == g['lin_%s_b' % name]).all()
+
+
+def test_tgsw(golden):
+    g = golden('tgsw')
+    accum_small, accum_full, tr_sample, bk = G.tgsw_inputs()
+    assert (O.tgsw_decompose(accum_full) == g['decomp']).all()
+    assert (O.tgsw_mac(tr_sample, bk, 1) == g['mac']).all()
+    assert (O.tgsw_external_mul(accum_small, bk, 2) == g['ext_small']).all()
+    assert (O.tgsw_external_mul(accum_full, bk, 0) == g['ext_full']).all()
+
+
+def test_keyswitch(golden):
+    g = golden('keyswitch')
+    ks_a, ks_b, ks_cv, src_a, src_b = G.keyswitch_inputs()
+    ra, rb, rcv = O.lwe_keyswitch(ks_a, ks_b, ks_cv, src_a, src_b)
+    assert (ra == g['res_a']).all() and (rb == g['res_b']).all()
+    assert numpy.allclose(rcv, g['res_cv'], rtol=1e-4, atol=1e-4)
+
+
+@pytest.fixture(scope='module')
+def keys():
+    return O.OracleKeys(G.GATE_SEED)
+
+
+def test_keygen_matches_reference(golden, keys):
+    g = golden('gate')
+    assert sha(keys.lwe_key) == str(g['lwe_key_sha'])
+    assert sha(keys.tlwe_key) == str(g['tlwe_key_sha'])
+    assert sha(keys.bk_raw) == str(g['bk_raw_sha'])
+    assert sha(keys.bk) == str(g['bk_sha'])
+    assert (keys.bk[0] == g['bk_row0']).all() and (keys.bk[499] == g['bk_row499']).all()
+    assert sha(keys.ks_a) == str(g['ks_a_sha'])
+    assert sha(keys.ks_b) == str(g['ks_b_sha'])
+
+
+def test_gate_nand_matches_reference(golden, keys):
+    g = golden('gate')
+    c1 = keys.encrypt(G.GATE_BITS_A)
+    c2 = keys.encrypt(G.GATE_BITS_B)
+    c3 = keys.encrypt(G.GATE_BITS_C)
+    assert (c1[0] == g['c1_a']).all() and (c1[1] == g['c1_b']).all()
+    assert (c3[0] == g['c3_a']).all() and (c3[1] == g['c3_b']).all()
+    sl = slice(0, 2)
+    num, den, sa, sb = O.GATE_TABLE['nand']
+    t = O.lwe_affine2((c1[0][sl], c1[1][sl]), (c2[0][sl], c2[1][sl]), O.phase_to_t32(num, den), sa, sb)
+    ext = O.bootstrap(t[0], t[1], keys.bk, None)
+    assert (ext[0] == g['nand_ext_a']).all() and (ext[1] == g['nand_ext_b']).all()
+    out = O.gate_binary('nand', (c1[0][sl], c1[1][sl]), (c2[0][sl], c2[1][sl]), keys.bk, keys.ks)
+    assert (out[0] == g['nand_a']).all() and (out[1] == g['nand_b']).all()
+    assert (keys.decrypt(out) == g['nand_bits']).all()
+
+
+def test_all_gates_truth_tables(keys):
+    a_bits = numpy.array(G.GATE_BITS_A)
+    b_bits = numpy.array(G.GATE_BITS_B)
+    c_bits = numpy.array(G.GATE_BITS_C)
+    a, b, c = keys.encrypt(a_bits), keys.encrypt(b_bits), keys.encrypt(c_bits)
+    truth = dict(
+        nand=~(a_bits & b_bits), xor=a_bits ^ b_bits, xnor=~(a_bits ^ b_bits), nor=~(a_bits | b_bits),
+        andny=~a_bits & b_bits, andyn=a_bits & ~b_bits, orny=~a_bits | b_bits, oryn=a_bits | ~b_bits)
+    truth['or'] = a_bits | b_bits
+    truth['and'] = a_bits & b_bits
+    for name, want in truth.items():
+        assert (keys.decrypt(O.gate_binary(name, a, b, keys.bk, keys.ks)) == want).all(), name
+    assert (keys.decrypt(O.gate_mux(a, b, c, keys.bk, keys.ks)) == numpy.where(a_bits, b_bits, c_bits)).all()
