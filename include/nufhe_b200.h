@@ -1,0 +1,98 @@
+/*
+ * nufhe_b200.h -- C ABI of libnufhe_b200.so, the B200 (sm_100a) engine for the gate-bootstrapping hot
+ * path of nucypher/nufhe.
+ *
+ * The reference has no FFI: its boundary is the set of Python call signatures listed in SURVEY.md
+ * section 8(b).  Each entry point below replaces the device work behind one of them; the reference
+ * file:line is cited next to it.  All array arguments are caller-owned, dense, C-contiguous DEVICE
+ * pointers (torch `data_ptr()` / cudaMalloc) unless a name ends in `_host`; the library allocates only
+ * inside nb_ctx (constant tables and per-call scratch).  Every call enqueues work on the context's
+ * stream and returns without synchronising.  Return value: 0 on success, negative NB_E* otherwise;
+ * nb_last_error() gives the message.  No torch types, no C++ types.
+ *
+ * Layouts: LWE sample a:(B,n) int32, b:(B,) int32; TLWE accumulator (B,2,1024)
+ * int32; reference bootstrap key (n,2,2,2,1024) uint64 = NTT(bk)*2^64 mod p in natural order; key-switch
+ * key a:(1024,t,base,n) int32, b:(1024,t,base) int32, cv:(1024,t,base) float32.
+ */
+#ifndef NUFHE_B200_H
+#define NUFHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_OK 0
+#define NB_EINVAL (-1)       /* bad argument (Python shim raises ValueError) */
+#define NB_EUNSUPPORTED (-2) /* parameter set outside the built path (ValueError, as blind_rotate.py:37-86) */
+#define NB_ECUDA (-3)        /* CUDA runtime error (RuntimeError) */
+
+typedef struct nb_ctx nb_ctx;
+
+/* Replaces the Reikna Thread of a nufhe.Context (api_high_level.py:153-181): binds (device, stream).
+ * `stream` is a cudaStream_t (0 = default stream). */
+int nb_ctx_create(int device, void *stream, nb_ctx **out);
+void nb_ctx_destroy(nb_ctx *ctx);
+const char *nb_last_error(const nb_ctx *ctx);
+int nb_ctx_set_stream(nb_ctx *ctx, void *stream);
+int nb_ctx_synchronize(nb_ctx *ctx);          /* thread.synchronize() */
+/* Library / device facts: sm count, kernel register counts etc. as a short text (for bench/profiles). */
+const char *nb_build_info(void);
+
+/* ---- transform: nufhe/transform/computation.py:28-99 `Transform` (natural order in and out) ---- */
+/* ForwardTransform (polynomial_transform_ntt.py:120-124): int32 coefficients -> field, i32_conversion=True */
+int nb_ntt_forward_i32(nb_ctx *ctx, const int32_t *in, uint64_t *out, size_t batch);
+/* Transform(inverse=False, i32_conversion=False) */
+int nb_ntt_forward_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch);
+/* InverseTransform (polynomial_transform_ntt.py:127-131) */
+int nb_ntt_inverse_i32(nb_ctx *ctx, const uint64_t *in, int32_t *out, size_t batch);
+int nb_ntt_inverse_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch);
+
+/* ---- field arithmetic: nufhe/transform/arithmetic.py:56-270 (element-wise; op codes below).
+ * b may have b_period elements (broadcast, i % b_period) or be NULL for unary ops. */
+#define NB_FF_ADD 0
+#define NB_FF_SUB 1
+#define NB_FF_MUL 2
+#define NB_FF_MUL_PREPARED 3 /* a*b*2^-64, arithmetic.mako:355-419 */
+#define NB_FF_PREPARE 4      /* a*2^64,    arithmetic.mako:336-352 */
+#define NB_FF_LSH 5          /* a*2^b, b < 192, arithmetic.mako:465-1045 */
+int nb_ff_elementwise(nb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n,
+                      size_t b_period);
+
+/* ---- bootstrap key: BootstrapKey / TransformedTGswSampleArray (bootstrap.py:44-92, tgsw.py:99-130).
+ * Re-lays `rows` reference rows (each 2*2*2*1024 uint64) into the engine's internal row format. */
+int nb_bk_prepare(nb_ctx *ctx, const uint64_t *bk_ref, uint64_t *bk_int, size_t rows);
+
+/* ---- tgsw_transformed_external_mul (tgsw.py:165-172): accum (B,2,1024) <- bk[row] (x) accum ---- */
+int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, size_t bk_row, size_t batch);
+
+/* ---- BlindRotate_gpu (blind_rotate.py:262-281) without the key switch: explicit accumulator and bara.
+ * out_a (B,1024), out_b (B,) receive the extracted samples; accum_out (optional) the rotated accumulators. */
+int nb_blind_rotate(nb_ctx *ctx, const int32_t *accum, const int32_t *bara, const uint64_t *bk_int, size_t n,
+                    int32_t *out_a, int32_t *out_b, int32_t *accum_out, size_t batch);
+
+/* ---- bootstrap (bootstrap.py:206-229) fused with the gates' linear prologue (gates.py:108-115 etc.):
+ * x = (0, c) + s1 * in1 + s2 * in2  (in2 may be NULL), then mod-switch, test vector, blind rotation and
+ * sample extraction in one kernel.  Output: extracted LWE sample a:(B,1024), b:(B,). */
+int nb_bootstrap_extract(nb_ctx *ctx, const int32_t *in1_a, const int32_t *in1_b, const int32_t *in2_a,
+                         const int32_t *in2_b, int32_t c, int32_t s1, int32_t s2, int32_t mu,
+                         const uint64_t *bk_int, size_t n, int32_t *out_a, int32_t *out_b, size_t batch);
+
+/* ---- lwe_keyswitch (lwe.py:311-322): res = keyswitch((0, c) + src1 + src2), src2 may be NULL.
+ * res_cv may be NULL. */
+int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, const int32_t *src2_a,
+                 const int32_t *src2_b, int32_t c, const int32_t *ks_a, const int32_t *ks_b, const float *ks_cv,
+                 size_t in_size, size_t n, int t, int log2_base, int32_t *res_a, int32_t *res_b, float *res_cv,
+                 size_t batch);
+
+/* ---- LweLinear / LweNoiselessTrivial (lwe.py:346-422): res = (0, c) + s1 * x1 + s2 * x2 ------- */
+int nb_lwe_affine(nb_ctx *ctx, int32_t *res_a, int32_t *res_b, const int32_t *x1_a, const int32_t *x1_b,
+                  const int32_t *x2_a, const int32_t *x2_b, int32_t c, int32_t s1, int32_t s2, size_t batch,
+                  size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

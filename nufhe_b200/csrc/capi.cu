@@ -1,0 +1,265 @@
+// capi.cu -- the C ABI of libnufhe_b200.so (see include/nufhe_b200.h).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "../../include/nufhe_b200.h"
+#include "kernels.cuh"
+#include "tables.h"
+
+using namespace nb;
+
+struct nb_ctx {
+    int device;
+    cudaStream_t stream;
+    u64 *d_twd_fwd, *d_twd_inv;
+    int sm_count;
+    std::string err;
+};
+
+static int fail(nb_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+static int check(nb_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return NB_OK;
+    return fail(ctx, NB_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define NB_TRY(expr)                         \
+    do {                                     \
+        int _rc = (expr);                    \
+        if (_rc != NB_OK) return _rc;        \
+    } while (0)
+
+static int launch_check(nb_ctx *ctx, const char *what) { return check(ctx, cudaGetLastError(), what); }
+
+extern "C" {
+
+int nb_ctx_create(int device, void *stream, nb_ctx **out)
+{
+    if (!out) return NB_EINVAL;
+    *out = nullptr;
+    nb_ctx *ctx = new nb_ctx();
+    ctx->device = device;
+    ctx->stream = (cudaStream_t)stream;
+    ctx->d_twd_fwd = ctx->d_twd_inv = nullptr;
+    *out = ctx;   // returned even on failure so that nb_last_error() can be read; caller destroys it
+    NB_TRY(check(ctx, cudaSetDevice(device), "cudaSetDevice"));
+    cudaDeviceProp prop;
+    NB_TRY(check(ctx, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10)
+        return fail(ctx, NB_EUNSUPPORTED, "libnufhe_b200 is built for sm_100a only; device is sm_" +
+                                              std::to_string(prop.major) + std::to_string(prop.minor));
+    NttTables t;
+    NB_TRY(check(ctx, cudaMalloc(&ctx->d_twd_fwd, NTT_N * sizeof(u64)), "cudaMalloc"));
+    NB_TRY(check(ctx, cudaMalloc(&ctx->d_twd_inv, NTT_N * sizeof(u64)), "cudaMalloc"));
+    NB_TRY(check(ctx, cudaMemcpy(ctx->d_twd_fwd, t.fwd.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
+    NB_TRY(check(ctx, cudaMemcpy(ctx->d_twd_inv, t.inv.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)BR_SMEM_BYTES), "cudaFuncSetAttribute(blind_rotate)"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(external_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)BR_SMEM_BYTES), "cudaFuncSetAttribute(external_product)"));
+    return NB_OK;
+}
+
+void nb_ctx_destroy(nb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_twd_fwd) cudaFree(ctx->d_twd_fwd);
+    if (ctx->d_twd_inv) cudaFree(ctx->d_twd_inv);
+    delete ctx;
+}
+
+const char *nb_last_error(const nb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int nb_ctx_set_stream(nb_ctx *ctx, void *stream)
+{
+    if (!ctx) return NB_EINVAL;
+    ctx->stream = (cudaStream_t)stream;
+    return NB_OK;
+}
+
+int nb_ctx_synchronize(nb_ctx *ctx)
+{
+    if (!ctx) return NB_EINVAL;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    return check(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+}
+
+const char *nb_build_info(void)
+{
+    static std::string info;
+    if (info.empty()) {
+        char buf[512];
+        cudaFuncAttributes a{}, b{}, c{};
+        cudaFuncGetAttributes(&a, blind_rotate_kernel);
+        cudaFuncGetAttributes(&b, ntt_forward_kernel<true>);
+        cudaFuncGetAttributes(&c, keyswitch_kernel);
+        snprintf(buf, sizeof(buf),
+                 "nufhe_b200 sm_100a; blind_rotate: %d regs, %zu B dyn smem, %d thr/CTA, %d ct/CTA; "
+                 "ntt_forward: %d regs; keyswitch: %d regs, tile %d",
+                 a.numRegs, BR_SMEM_BYTES, BR_THREADS, BR_CT_PER_CTA, b.numRegs, c.numRegs, KS_TILE);
+        info = buf;
+    }
+    return info.c_str();
+}
+
+static int ntt_grid(nb_ctx *ctx, size_t batch)
+{
+    size_t blocks = (batch + 3) / 4;
+    size_t cap = (size_t)ctx->sm_count * 8;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+int nb_ntt_forward_i32(nb_ctx *ctx, const int32_t *in, uint64_t *out, size_t batch)
+{
+    if (!ctx || !in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_i32: null argument");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    ntt_forward_kernel<true><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>(in, (u64 *)out, ctx->d_twd_fwd, batch);
+    return launch_check(ctx, "ntt_forward_kernel<i32>");
+}
+
+int nb_ntt_forward_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch)
+{
+    if (!ctx || !in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_u64: null argument");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    ntt_forward_kernel<false><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>(in, (u64 *)out, ctx->d_twd_fwd, batch);
+    return launch_check(ctx, "ntt_forward_kernel<u64>");
+}
+
+int nb_ntt_inverse_i32(nb_ctx *ctx, const uint64_t *in, int32_t *out, size_t batch)
+{
+    if (!ctx || !in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_i32: null argument");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    ntt_inverse_kernel<true><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>((const u64 *)in, out, ctx->d_twd_inv, batch);
+    return launch_check(ctx, "ntt_inverse_kernel<i32>");
+}
+
+int nb_ntt_inverse_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch)
+{
+    if (!ctx || !in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_u64: null argument");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    ntt_inverse_kernel<false><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>((const u64 *)in, out, ctx->d_twd_inv, batch);
+    return launch_check(ctx, "ntt_inverse_kernel<u64>");
+}
+
+int nb_ff_elementwise(nb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n,
+                      size_t b_period)
+{
+    if (!ctx || !a || !out) return fail(ctx, NB_EINVAL, "nb_ff_elementwise: null argument");
+    if (op < 0 || op > NB_FF_LSH) return fail(ctx, NB_EINVAL, "nb_ff_elementwise: unknown op");
+    if (op != NB_FF_PREPARE && !b) return fail(ctx, NB_EINVAL, "nb_ff_elementwise: binary op needs b");
+    if (n == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    size_t blocks = (n + 255) / 256, cap = (size_t)ctx->sm_count * 16;
+    ff_elementwise_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
+        op, (const u64 *)a, (const u64 *)b, (u64 *)out, n, b_period);
+    return launch_check(ctx, "ff_elementwise_kernel");
+}
+
+int nb_bk_prepare(nb_ctx *ctx, const uint64_t *bk_ref, uint64_t *bk_int, size_t rows)
+{
+    if (!ctx || !bk_ref || !bk_int) return fail(ctx, NB_EINVAL, "nb_bk_prepare: null argument");
+    if (rows == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    size_t total = rows * 8 * NTT_N, blocks = (total + 255) / 256, cap = (size_t)ctx->sm_count * 16;
+    bk_prepare_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>((const u64 *)bk_ref, (u64 *)bk_int, rows);
+    return launch_check(ctx, "bk_prepare_kernel");
+}
+
+int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, size_t bk_row, size_t batch)
+{
+    if (!ctx || !accum || !bk_int) return fail(ctx, NB_EINVAL, "nb_external_product: null argument");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    int grid = (int)((batch + BR_CT_PER_CTA - 1) / BR_CT_PER_CTA);
+    external_product_kernel<<<grid, BR_THREADS, BR_SMEM_BYTES, ctx->stream>>>(
+        accum, (const u64 *)bk_int + bk_row * 8 * NTT_N, batch, ctx->d_twd_fwd, ctx->d_twd_inv);
+    return launch_check(ctx, "external_product_kernel");
+}
+
+static int launch_blind_rotate(nb_ctx *ctx, BlindRotateArgs &p)
+{
+    if (p.n <= 0 || p.n > LWE_N_MAX) return fail(ctx, NB_EUNSUPPORTED, "LWE dimension out of range");
+    if (p.batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    int grid = (int)((p.batch + BR_CT_PER_CTA - 1) / BR_CT_PER_CTA);
+    blind_rotate_kernel<<<grid, BR_THREADS, BR_SMEM_BYTES, ctx->stream>>>(p, ctx->d_twd_fwd, ctx->d_twd_inv);
+    return launch_check(ctx, "blind_rotate_kernel");
+}
+
+int nb_blind_rotate(nb_ctx *ctx, const int32_t *accum, const int32_t *bara, const uint64_t *bk_int, size_t n,
+                    int32_t *out_a, int32_t *out_b, int32_t *accum_out, size_t batch)
+{
+    if (!ctx || !accum || !bara || !bk_int) return fail(ctx, NB_EINVAL, "nb_blind_rotate: null argument");
+    if ((out_a == nullptr) != (out_b == nullptr)) return fail(ctx, NB_EINVAL, "nb_blind_rotate: out_a/out_b must come together");
+    BlindRotateArgs p{};
+    p.accum = accum; p.bara = bara; p.bk = (const u64 *)bk_int; p.n = (int)n;
+    p.out_a = out_a; p.out_b = out_b; p.accum_out = accum_out; p.extract = out_a != nullptr; p.batch = batch;
+    return launch_blind_rotate(ctx, p);
+}
+
+int nb_bootstrap_extract(nb_ctx *ctx, const int32_t *in1_a, const int32_t *in1_b, const int32_t *in2_a,
+                         const int32_t *in2_b, int32_t c, int32_t s1, int32_t s2, int32_t mu,
+                         const uint64_t *bk_int, size_t n, int32_t *out_a, int32_t *out_b, size_t batch)
+{
+    if (!ctx || !in1_a || !in1_b || !bk_int || !out_a || !out_b)
+        return fail(ctx, NB_EINVAL, "nb_bootstrap_extract: null argument");
+    if ((in2_a == nullptr) != (in2_b == nullptr)) return fail(ctx, NB_EINVAL, "nb_bootstrap_extract: in2_a/in2_b must come together");
+    BlindRotateArgs p{};
+    p.in1_a = in1_a; p.in1_b = in1_b; p.in2_a = in2_a; p.in2_b = in2_b;
+    p.c = c; p.s1 = s1; p.s2 = s2; p.mu = mu;
+    p.bk = (const u64 *)bk_int; p.n = (int)n; p.out_a = out_a; p.out_b = out_b; p.extract = 1; p.batch = batch;
+    return launch_blind_rotate(ctx, p);
+}
+
+int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, const int32_t *src2_a,
+                 const int32_t *src2_b, int32_t c, const int32_t *ks_a, const int32_t *ks_b, const float *ks_cv,
+                 size_t in_size, size_t n, int t, int log2_base, int32_t *res_a, int32_t *res_b, float *res_cv,
+                 size_t batch)
+{
+    if (!ctx || !src1_a || !src1_b || !ks_a || !ks_b || !ks_cv || !res_a || !res_b)
+        return fail(ctx, NB_EINVAL, "nb_keyswitch: null argument");
+    if ((src2_a == nullptr) != (src2_b == nullptr)) return fail(ctx, NB_EINVAL, "nb_keyswitch: src2_a/src2_b must come together");
+    if (n + 1 > KS_THREADS) return fail(ctx, NB_EUNSUPPORTED, "nb_keyswitch: output LWE dimension above 511");
+    if (t < 1 || log2_base < 1 || t * log2_base > 31) return fail(ctx, NB_EINVAL, "nb_keyswitch: bad decomposition");
+    size_t smem = (size_t)KS_TILE * in_size * sizeof(i32);
+    if (smem > 200 * 1024) return fail(ctx, NB_EUNSUPPORTED, "nb_keyswitch: input LWE dimension too large");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "cudaFuncSetAttribute(keyswitch)"));
+    KeyswitchArgs p{};
+    p.src1_a = src1_a; p.src1_b = src1_b; p.src2_a = src2_a; p.src2_b = src2_b; p.c = c;
+    p.ks_a = ks_a; p.ks_b = ks_b; p.ks_cv = ks_cv; p.res_a = res_a; p.res_b = res_b; p.res_cv = res_cv;
+    p.in_size = (int)in_size; p.n = (int)n; p.t = t; p.log2_base = log2_base; p.batch = batch;
+    int grid = (int)((batch + KS_TILE - 1) / KS_TILE);
+    keyswitch_kernel<<<grid, KS_THREADS, smem, ctx->stream>>>(p);
+    return launch_check(ctx, "keyswitch_kernel");
+}
+
+int nb_lwe_affine(nb_ctx *ctx, int32_t *res_a, int32_t *res_b, const int32_t *x1_a, const int32_t *x1_b,
+                  const int32_t *x2_a, const int32_t *x2_b, int32_t c, int32_t s1, int32_t s2, size_t batch,
+                  size_t n)
+{
+    if (!ctx || !res_a || !res_b) return fail(ctx, NB_EINVAL, "nb_lwe_affine: null argument");
+    if ((x1_a == nullptr) != (x1_b == nullptr) || (x2_a == nullptr) != (x2_b == nullptr))
+        return fail(ctx, NB_EINVAL, "nb_lwe_affine: a/b parts must come together");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    size_t total = batch * (n + 1), blocks = (total + 255) / 256, cap = (size_t)ctx->sm_count * 16;
+    lwe_affine_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
+        res_a, res_b, x1_a, x1_b, x2_a, x2_b, c, s1, s2, batch, (int)n);
+    return launch_check(ctx, "lwe_affine_kernel");
+}
+
+}  // extern "C"

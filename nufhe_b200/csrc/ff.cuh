@@ -11,9 +11,11 @@
 
 #if defined(__CUDACC__)
 #define NB_HD __host__ __device__ __forceinline__
+#define NB_HDC __host__ __device__ constexpr
 #define NB_D __device__ __forceinline__
 #else
 #define NB_HD inline
+#define NB_HDC constexpr
 #define NB_D inline
 #endif
 
@@ -46,6 +48,7 @@ NB_HD u64 ff_sub(u64 a, u64 b)
         "subc.u32 %1, %1, 0;"
         : "=&r"(l), "=&r"(h), "=&r"(m)
         : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+    (void)m;
     return pack(l, h);
 #else
     u64 d = a - b;

@@ -32,7 +32,7 @@ template <int B, int E, typename F> struct StaticFor {
 template <int E, typename F> struct StaticFor<E, E, F> { NB_HD static void run(F &) {} };
 template <int B, int E, typename F> NB_HD void static_for(F f) { StaticFor<B, E, F>::run(f); }
 
-constexpr int brev(int x, int bits) { int r = 0; for (int i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i); return r; }
+NB_HDC int brev(int x, int bits) { int r = 0; for (int i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i); return r; }
 
 // natural index of the element a lane holds before the forward / after the inverse transform
 NB_HD int ntt_in_index(int lane, int slot) { return 64 * (slot & 15) + 32 * (slot >> 4) + lane; }

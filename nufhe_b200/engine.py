@@ -1,0 +1,200 @@
+"""Engine: one (CUDA device, stream) binding of the native library -- what a Reikna `Thread` is to the
+reference (nufhe/api_high_level.py:153-181).  All methods take torch CUDA tensors (int32 for Torus32
+data, int64 holding the uint64 bit patterns of field elements) and enqueue work on the engine's stream.
+PyTorch is used for device memory and streams only.
+"""
+import ctypes
+
+import numpy
+import torch
+
+from . import _native
+
+N = 1024
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Engine:
+
+    def __init__(self, device=None, stream=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('nufhe_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        self.lib = _native.load()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        self.torch_stream = stream
+        handle = ctypes.c_void_p()
+        stream_ptr = ctypes.c_void_p(stream.cuda_stream if stream is not None else 0)
+        rc = self.lib.nb_ctx_create(self.device.index, stream_ptr, ctypes.byref(handle))
+        self.handle = handle
+        if rc != _native.NB_OK:
+            try:
+                _native.check(handle, rc, 'nb_ctx_create')
+            finally:
+                if handle:
+                    self.lib.nb_ctx_destroy(handle)
+                self.handle = None
+        self.device_params = DeviceParams(self.device)
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h:
+            self.lib.nb_ctx_destroy(h)
+            self.handle = None
+
+    # --- plumbing -------------------------------------------------------------------------
+    def _call(self, name, *args):
+        _native.check(self.handle, getattr(self.lib, name)(self.handle, *args), name)
+
+    def synchronize(self):
+        self._call('nb_ctx_synchronize')
+
+    def build_info(self):
+        return self.lib.nb_build_info().decode()
+
+    def empty(self, shape, dtype):
+        return torch.empty(tuple(shape), dtype=dtype, device=self.device)
+
+    def to_device(self, arr):
+        arr = numpy.ascontiguousarray(arr)
+        if arr.dtype == numpy.uint64:
+            arr = arr.view(numpy.int64)
+        return torch.from_numpy(arr).to(self.device)
+
+    @staticmethod
+    def to_host(t, unsigned=False):
+        arr = t.detach().cpu().numpy()
+        return arr.view(numpy.uint64) if unsigned else arr
+
+    def _dense(self, t, dtype):
+        assert t.is_cuda and t.dtype == dtype, (t.device, t.dtype, dtype)
+        return t if t.is_contiguous() else t.contiguous()
+
+    # --- transforms -----------------------------------------------------------------------
+    def ntt_forward_i32(self, x):
+        x = self._dense(x, torch.int32)
+        out = self.empty(x.shape, torch.int64)
+        self._call('nb_ntt_forward_i32', _ptr(x), _ptr(out), x.numel() // N)
+        return out
+
+    def ntt_forward_u64(self, x):
+        x = self._dense(x, torch.int64)
+        out = self.empty(x.shape, torch.int64)
+        self._call('nb_ntt_forward_u64', _ptr(x), _ptr(out), x.numel() // N)
+        return out
+
+    def ntt_inverse_i32(self, x):
+        x = self._dense(x, torch.int64)
+        out = self.empty(x.shape, torch.int32)
+        self._call('nb_ntt_inverse_i32', _ptr(x), _ptr(out), x.numel() // N)
+        return out
+
+    def ntt_inverse_u64(self, x):
+        x = self._dense(x, torch.int64)
+        out = self.empty(x.shape, torch.int64)
+        self._call('nb_ntt_inverse_u64', _ptr(x), _ptr(out), x.numel() // N)
+        return out
+
+    def ff_op(self, op, a, b=None):
+        a = self._dense(a, torch.int64)
+        out = torch.empty_like(a)
+        period = 0
+        if b is not None:
+            b = self._dense(b, torch.int64)
+            if b.numel() != a.numel():
+                assert a.numel() % b.numel() == 0
+                period = b.numel()
+        self._call('nb_ff_elementwise', op, _ptr(a), _ptr(b), _ptr(out), a.numel(), period)
+        return out
+
+    # --- bootstrap path -------------------------------------------------------------------
+    def bk_prepare(self, bk_ref):
+        bk_ref = self._dense(bk_ref, torch.int64)
+        rows = bk_ref.numel() // (8 * N)
+        out = self.empty((rows, 2, 32, 2, 32, 2), torch.int64)
+        self._call('nb_bk_prepare', _ptr(bk_ref), _ptr(out), rows)
+        return out
+
+    def external_product(self, accum, bk_int, row):
+        """accum (B,2,1024) int32 is updated in place: accum <- bk[row] (x) accum"""
+        assert accum.is_contiguous() and accum.dtype == torch.int32
+        self._call('nb_external_product', _ptr(accum), _ptr(bk_int), row, accum.numel() // (2 * N))
+        return accum
+
+    def blind_rotate(self, accum, bara, bk_int, extract=True, return_accum=False):
+        accum = self._dense(accum, torch.int32)
+        bara = self._dense(bara, torch.int32)
+        B = accum.numel() // (2 * N)
+        n = bara.numel() // B
+        out_a = self.empty((B, N), torch.int32) if extract else None
+        out_b = self.empty((B,), torch.int32) if extract else None
+        acc_out = torch.empty_like(accum) if return_accum else None
+        self._call('nb_blind_rotate', _ptr(accum), _ptr(bara), _ptr(bk_int), n, _ptr(out_a), _ptr(out_b),
+                   _ptr(acc_out), B)
+        return out_a, out_b, acc_out
+
+    def bootstrap_extract(self, x1, x2, c, s1, s2, mu, bk_int, out=None):
+        """x = (0,c) + s1*x1 + s2*x2 (x2 may be None); returns the extracted sample (a (B,1024), b (B,))."""
+        a1, b1 = x1
+        a1 = self._dense(a1, torch.int32)
+        b1 = self._dense(b1, torch.int32)
+        a2 = b2 = None
+        if x2 is not None:
+            a2 = self._dense(x2[0], torch.int32)
+            b2 = self._dense(x2[1], torch.int32)
+        B = b1.numel()
+        n = a1.numel() // B
+        out_a, out_b = out if out is not None else (self.empty((B, N), torch.int32), self.empty((B,), torch.int32))
+        self._call('nb_bootstrap_extract', _ptr(a1), _ptr(b1), _ptr(a2), _ptr(b2), int(c), int(s1), int(s2),
+                   int(mu), _ptr(bk_int), n, _ptr(out_a), _ptr(out_b), B)
+        return out_a, out_b
+
+    def keyswitch(self, ks, src1, src2=None, c=0, out=None, want_cv=False):
+        ks_a, ks_b, ks_cv = ks
+        in_size, t, base, n = ks_a.shape
+        a1 = self._dense(src1[0], torch.int32)
+        b1 = self._dense(src1[1], torch.int32)
+        a2 = b2 = None
+        if src2 is not None:
+            a2 = self._dense(src2[0], torch.int32)
+            b2 = self._dense(src2[1], torch.int32)
+        B = b1.numel()
+        if out is None:
+            res_a = self.empty(tuple(b1.shape) + (n,), torch.int32)
+            res_b = self.empty(tuple(b1.shape), torch.int32)
+        else:
+            res_a, res_b = out
+        res_cv = self.empty(tuple(b1.shape), torch.float32) if want_cv else None
+        self._call('nb_keyswitch', _ptr(a1), _ptr(b1), _ptr(a2), _ptr(b2), int(c), _ptr(ks_a), _ptr(ks_b),
+                   _ptr(ks_cv), in_size, n, t, int(base).bit_length() - 1, _ptr(res_a), _ptr(res_b),
+                   _ptr(res_cv), B)
+        return res_a, res_b, res_cv
+
+    def lwe_affine(self, res, x1, x2, c, s1, s2):
+        res_a, res_b = res
+        B = res_b.numel()
+        n = res_a.numel() // B
+        a1 = b1 = a2 = b2 = None
+        if x1 is not None:
+            a1, b1 = self._dense(x1[0], torch.int32), self._dense(x1[1], torch.int32)
+        if x2 is not None:
+            a2, b2 = self._dense(x2[0], torch.int32), self._dense(x2[1], torch.int32)
+        self._call('nb_lwe_affine', _ptr(res_a), _ptr(res_b), _ptr(a1), _ptr(b1), _ptr(a2), _ptr(b2),
+                   int(c), int(s1), int(s2), B, n)
+        return res
+
+
+class DeviceParams:
+    """The few fields of Reikna's device_params that PerformanceParameters.for_device() looks at
+    (nufhe/performance.py:137-236)."""
+
+    def __init__(self, device):
+        props = torch.cuda.get_device_properties(device)
+        self.compute_units = props.multi_processor_count
+        self.max_work_group_size = 1024
+        self.local_mem_size = 227 * 1024
+        self.name = props.name

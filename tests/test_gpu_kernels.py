@@ -1,0 +1,166 @@
+"""Kernel-level parity: CUDA (through the C ABI) == CPU oracle == reference golden vectors, bit for bit.
+Mirrors the reference's per-kernel tests (test/test_transform/test_computation.py, test_arithmetic.py,
+test_tgsw.py, test_lwe.py, test_tlwe.py)."""
+import numpy
+import pytest
+import torch
+
+import gen_inputs as G
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from nufhe_b200.engine import Engine
+    return Engine()
+
+
+def dev_u64(eng, arr):
+    return eng.to_device(numpy.ascontiguousarray(arr, numpy.uint64))
+
+
+def test_arithmetic(eng, golden):
+    from nufhe_b200 import _native as nv
+    g = golden('arithmetic')
+    a, b, s = G.arithmetic_inputs()
+    da, db = dev_u64(eng, a), dev_u64(eng, b)
+    for op, key in ((nv.FF_MUL, 'mul'), (nv.FF_ADD, 'add'), (nv.FF_SUB, 'sub'), (nv.FF_MUL_PREPARED, 'mul_prepared')):
+        assert (eng.to_host(eng.ff_op(op, da, db), True) == g[key]).all(), key
+    assert (eng.to_host(eng.ff_op(nv.FF_PREPARE, da), True) == g['prepare_for_mul']).all()
+    ds = dev_u64(eng, s.astype(numpy.uint64))
+    assert (eng.to_host(eng.ff_op(nv.FF_LSH, da, ds), True) == g['lsh']).all()
+
+
+def test_arithmetic_random_vs_oracle(eng):
+    from nufhe_b200 import _native as nv
+    rng = G.rs(11)
+    a, b = G.ff_numbers(rng, (1 << 16,)), G.ff_numbers(rng, (1 << 16,))
+    da, db = dev_u64(eng, a), dev_u64(eng, b)
+    assert (eng.to_host(eng.ff_op(nv.FF_MUL, da, db), True) == O.ff_mul(a, b)).all()
+    assert (eng.to_host(eng.ff_op(nv.FF_ADD, da, db), True) == O.ff_add(a, b)).all()
+    assert (eng.to_host(eng.ff_op(nv.FF_SUB, da, db), True) == O.ff_sub(a, b)).all()
+    s = rng.randint(0, 192, size=a.shape).astype(numpy.uint64)
+    assert (eng.to_host(eng.ff_op(nv.FF_LSH, da, dev_u64(eng, s)), True) == O.ff_lsh(a, s.astype(numpy.uint32))).all()
+
+
+def test_ntt_golden(eng, golden):
+    g = golden('ntt')
+    x_i32, x_u64 = G.ntt_inputs()
+    assert (eng.to_host(eng.ntt_forward_i32(eng.to_device(x_i32)), True) == g['fwd_i32']).all()
+    assert (eng.to_host(eng.ntt_forward_u64(dev_u64(eng, x_u64)), True) == g['fwd_u64']).all()
+    assert (eng.to_host(eng.ntt_inverse_u64(dev_u64(eng, x_u64)), True) == g['inv_u64']).all()
+    assert (eng.to_host(eng.ntt_inverse_i32(dev_u64(eng, x_u64))) == g['inv_i32']).all()
+
+
+@pytest.mark.parametrize('batch', [1, 3, 257, 5000])
+def test_ntt_vs_oracle(eng, batch):
+    rng = G.rs(200 + batch)
+    x = G.torus32(rng, (batch, 1024))
+    f = eng.ntt_forward_i32(eng.to_device(x))
+    ref = O.ntt_forward_i32(x)
+    assert (eng.to_host(f, True) == ref).all()
+    assert (eng.to_host(eng.ntt_inverse_i32(f)) == x).all()
+    y = G.ff_numbers(rng, (batch, 1024))
+    assert (eng.to_host(eng.ntt_inverse_u64(dev_u64(eng, y)), True) == O.ntt_inverse_u64(y)).all()
+
+
+def test_ntt_empty_batch(eng):
+    out = eng.ntt_forward_i32(eng.empty((0, 1024), torch.int32))
+    assert out.shape == (0, 1024)
+
+
+def test_ntt_convolution_property(eng):
+    # NTT -> pointwise product -> INTT == negacyclic product mod 2^32 (test_computation.py:71-124)
+    from nufhe_b200 import _native as nv
+    rng = G.rs(12)
+    a = G.torus32(rng, (8, 1024))
+    b = G.torus32(rng, (8, 1024), -1000, 1000)
+    fa, fb = eng.ntt_forward_i32(eng.to_device(a)), eng.ntt_forward_i32(eng.to_device(b))
+    prod = eng.to_host(eng.ntt_inverse_i32(eng.ff_op(nv.FF_MUL, fa, fb)))
+    assert (prod == O.poly_mul_i32(b[0], a)[0:1]).all() or True   # shape smoke; exact check below
+    for q in range(8):
+        full = numpy.convolve(a[q].astype(object), b[q].astype(object))
+        neg = full[:1024].copy()
+        neg[:1023] -= full[1024:]
+        want = numpy.array([int(v) % 2**32 for v in neg], numpy.uint64).astype(numpy.uint32)
+        assert (prod[q].view(numpy.uint32) == want).all()
+
+
+def test_external_product_golden(eng, golden):
+    g = golden('tgsw')
+    accum_small, accum_full, tr_sample, bk = G.tgsw_inputs()
+    bk_int = eng.bk_prepare(dev_u64(eng, bk))
+    acc = eng.to_device(accum_small)
+    assert (eng.to_host(eng.external_product(acc, bk_int, 2)) == g['ext_small']).all()
+    acc = eng.to_device(accum_full)
+    assert (eng.to_host(eng.external_product(acc, bk_int, 0)) == g['ext_full']).all()
+
+
+@pytest.mark.parametrize('batch', [1, 4, 5, 67])
+def test_external_product_vs_oracle(eng, batch):
+    rng = G.rs(300 + batch)
+    bk = G.ff_numbers(rng, (2, 2, 2, 2, 1024))
+    accum = G.torus32(rng, (batch, 2, 1024))
+    bk_int = eng.bk_prepare(dev_u64(eng, bk))
+    got = eng.to_host(eng.external_product(eng.to_device(accum), bk_int, 1))
+    assert (got == O.tgsw_external_mul(accum, bk, 1)).all()
+
+
+def test_blind_rotate_explicit_vs_oracle(eng):
+    # BlindRotate_gpu semantics with an explicit accumulator / bara and a short random-field key
+    rng = G.rs(13)
+    n, B = 6, 5
+    bk = G.ff_numbers(rng, (n, 2, 2, 2, 1024))
+    accum = G.torus32(rng, (B, 2, 1024))
+    bara = G.torus32(rng, (B, n), 0, 2048)
+    bara[0, :4] = [0, 1024, 1023, 2047]
+    bk_int = eng.bk_prepare(dev_u64(eng, bk))
+    out_a, out_b, acc_out = eng.blind_rotate(eng.to_device(accum), eng.to_device(bara), bk_int, return_accum=True)
+    want = O.blind_rotate(accum, bk, bara)
+    assert (eng.to_host(acc_out) == want).all()
+    ea, eb = O.tlwe_extract_lwe_samples(want)
+    assert (eng.to_host(out_a) == ea).all() and (eng.to_host(out_b) == eb).all()
+
+
+def test_keyswitch_golden(eng, golden):
+    g = golden('keyswitch')
+    ks_a, ks_b, ks_cv, src_a, src_b = G.keyswitch_inputs()
+    ks = (eng.to_device(ks_a), eng.to_device(ks_b), eng.to_device(ks_cv))
+    ra, rb, rcv = eng.keyswitch(ks, (eng.to_device(src_a), eng.to_device(src_b)), want_cv=True)
+    assert (eng.to_host(ra) == g['res_a']).all() and (eng.to_host(rb) == g['res_b']).all()
+    assert numpy.allclose(eng.to_host(rcv), g['res_cv'], rtol=1e-4, atol=1e-4)
+
+
+def test_keyswitch_ragged_batches(eng):
+    ks_a, ks_b, ks_cv, _, _ = G.keyswitch_inputs()
+    ks = (eng.to_device(ks_a), eng.to_device(ks_b), eng.to_device(ks_cv))
+    rng = G.rs(14)
+    for B in (1, 7, 8, 9, 33):
+        src_a, src_b = G.torus32(rng, (B, 1024)), G.torus32(rng, (B,))
+        src2_a, src2_b = G.torus32(rng, (B, 1024)), G.torus32(rng, (B,))
+        ra, rb, _ = eng.keyswitch(ks, (eng.to_device(src_a), eng.to_device(src_b)))
+        wa, wb, _ = O.lwe_keyswitch(ks_a, ks_b, ks_cv, src_a, src_b)
+        assert (eng.to_host(ra) == wa).all() and (eng.to_host(rb) == wb).all()
+        # fused (0,c) + src1 + src2 prologue used by gate_mux
+        ra, rb, _ = eng.keyswitch(ks, (eng.to_device(src_a), eng.to_device(src_b)),
+                                  (eng.to_device(src2_a), eng.to_device(src2_b)), c=2**29)
+        with numpy.errstate(over='ignore'):
+            sa = (src_a + src2_a).astype(numpy.int32)
+            sb = (src_b + src2_b + numpy.int32(2**29)).astype(numpy.int32)
+        wa, wb, _ = O.lwe_keyswitch(ks_a, ks_b, ks_cv, sa, sb)
+        assert (eng.to_host(ra) == wa).all() and (eng.to_host(rb) == wb).all()
+
+
+def test_lwe_affine(eng, golden):
+    g = golden('small')
+    a, b = G.linear_inputs()
+    da = (eng.to_device(a[0]), eng.to_device(a[1]))
+    db = (eng.to_device(b[0]), eng.to_device(b[1]))
+    for name in ('nand', 'xor', 'andny'):
+        num, den, sa, sb = O.GATE_TABLE[name]
+        res = (torch.empty_like(da[0]), torch.empty_like(da[1]))
+        eng.lwe_affine(res, da, db, O.phase_to_t32(num, den), sa, sb)
+        assert (eng.to_host(res[0]) == g['lin_%s_a' % name]).all()
+        assert (eng.to_host(res[1]) == g['lin_%s_b' % name]).all()
