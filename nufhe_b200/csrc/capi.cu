@@ -118,8 +118,9 @@ static int ntt_grid(nb_ctx *ctx, size_t batch)
 
 int nb_ntt_forward_i32(nb_ctx *ctx, const int32_t *in, uint64_t *out, size_t batch)
 {
-    if (!ctx || !in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_i32: null argument");
+    if (!ctx) return NB_EINVAL;
     if (batch == 0) return NB_OK;
+    if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_i32: null argument");
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
     ntt_forward_kernel<true><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>(in, (u64 *)out, ctx->d_twd_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<i32>");
@@ -127,8 +128,9 @@ int nb_ntt_forward_i32(nb_ctx *ctx, const int32_t *in, uint64_t *out, size_t bat
 
 int nb_ntt_forward_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch)
 {
-    if (!ctx || !in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_u64: null argument");
+    if (!ctx) return NB_EINVAL;
     if (batch == 0) return NB_OK;
+    if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_u64: null argument");
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
     ntt_forward_kernel<false><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>(in, (u64 *)out, ctx->d_twd_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<u64>");
@@ -136,8 +138,9 @@ int nb_ntt_forward_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
 
 int nb_ntt_inverse_i32(nb_ctx *ctx, const uint64_t *in, int32_t *out, size_t batch)
 {
-    if (!ctx || !in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_i32: null argument");
+    if (!ctx) return NB_EINVAL;
     if (batch == 0) return NB_OK;
+    if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_i32: null argument");
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
     ntt_inverse_kernel<true><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>((const u64 *)in, out, ctx->d_twd_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<i32>");
@@ -145,8 +148,9 @@ int nb_ntt_inverse_i32(nb_ctx *ctx, const uint64_t *in, int32_t *out, size_t bat
 
 int nb_ntt_inverse_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch)
 {
-    if (!ctx || !in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_u64: null argument");
+    if (!ctx) return NB_EINVAL;
     if (batch == 0) return NB_OK;
+    if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_u64: null argument");
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
     ntt_inverse_kernel<false><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>((const u64 *)in, out, ctx->d_twd_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<u64>");
