@@ -1,0 +1,146 @@
+"""Homomorphic gates (reference: nufhe/gates.py).
+
+Every bootstrapped binary gate is "(0, c) + s_a * a + s_b * b, then bootstrap" (gates.py:108-121 and
+its siblings); the constants below are the reference's, and the linear part is folded into the head of
+the bootstrap kernel instead of being three separate launches."""
+import numpy
+
+from .numeric_functions import phase_to_t32
+from .lwe import (
+    LweSampleArray, lwe_negate, lwe_copy, lwe_noiseless_trivial, _keyswitch_into)
+from .bootstrap import bootstrap_affine
+from .performance import PerformanceParameters, PerformanceParametersForDevice
+
+
+def get_shape(obj):
+    if hasattr(obj, 'shape'):
+        return tuple(obj.shape)
+    elif isinstance(obj, list):
+        return numpy.asarray(obj).shape
+    else:
+        raise ValueError("An object of type " + str(type(obj)) + " is not array-like")
+
+
+def _result_shape_pair(shape1, shape2):
+    if len(shape1) > len(shape2):
+        shape2 = (1,) * (len(shape1) - len(shape2)) + shape2
+    else:
+        shape1 = (1,) * (len(shape2) - len(shape1)) + shape1
+    if any((l1 != l2 and l1 > 1 and l2 > 1) for l1, l2 in zip(shape1, shape2)):
+        raise ValueError("Incompatible shapes: {s1}, {s2}".format(s1=shape1, s2=shape2))
+    return tuple((l1 if l1 > 1 else l2) for l1, l2 in zip(shape1, shape2))
+
+
+def result_shape(*shapes):
+    shapes = [tuple(s) for s in shapes]
+    if len(shapes) == 1:
+        return shapes[0]
+    elif len(shapes) == 2:
+        return _result_shape_pair(*shapes)
+    else:
+        return _result_shape_pair(shapes[0], result_shape(*shapes[1:]))
+
+
+def check_shape(result, *args):
+    rshape = result_shape(*[arg.shape for arg in args])
+    if len(rshape) > len(result.shape) or rshape != tuple(result.shape[len(result.shape) - len(rshape):]):
+        raise ValueError(
+            ("The shape of the result derived from the arguments {derived_shape} "
+             "cannot be broadcasted to the shape of the destination {dest_shape}").format(
+                derived_shape=rshape, dest_shape=tuple(result.shape)))
+
+
+MU = phase_to_t32(1, 8)
+
+# name -> (constant numerator, denominator, sign of a, sign of b); gates.py:81-597
+_BINARY_GATES = {
+    'nand': (1, 8, -1, -1),     # gates.py:108-115
+    'or': (1, 8, 1, 1),         # :150-157
+    'and': (-1, 8, 1, 1),       # :192-199
+    'xor': (1, 4, 2, 2),        # :234-241
+    'xnor': (-1, 4, -2, -2),    # :276-283
+    'nor': (-1, 8, -1, -1),     # :415-422
+    'andny': (-1, 8, -1, 1),    # :457-464
+    'andyn': (-1, 8, 1, -1),    # :499-506
+    'orny': (1, 8, -1, 1),      # :541-548
+    'oryn': (1, 8, 1, -1),      # :583-590
+}
+
+
+def _binary_gate(name, thr, cloud_key, result, a, b, perf_params):
+    check_shape(result, a, b)
+    num, den, sa, sb = _BINARY_GATES[name]
+    bootstrap_affine(
+        thr, result, cloud_key.bootstrap_key, cloud_key.keyswitch_key, MU,
+        a, b, phase_to_t32(num, den), sa, sb)
+
+
+def _make_binary(name, doc):
+    def gate(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, b: LweSampleArray,
+             perf_params: PerformanceParametersForDevice = None):
+        _binary_gate(name, thr, cloud_key, result, a, b, perf_params)
+    gate.__name__ = 'gate_' + name
+    gate.__doc__ = doc + """
+
+    The shapes of ``a`` and ``b`` should be broadcastable to the shape of ``result``.
+
+    :param thr: the engine (analogue of a ``reikna`` ``Thread``).
+    :param cloud_key: the cloud key.
+    :param result: an empty ciphertext where the result will be stored.
+    :param a: the ciphertext with the first argument.
+    :param b: the ciphertext with the second argument.
+    :param perf_params: accepted for API compatibility.
+    """
+    return gate
+
+
+gate_nand = _make_binary('nand', "Homomorphic bootstrapped NAND gate.")
+gate_or = _make_binary('or', "Homomorphic bootstrapped OR gate.")
+gate_and = _make_binary('and', "Homomorphic bootstrapped AND gate.")
+gate_xor = _make_binary('xor', "Homomorphic bootstrapped XOR gate.")
+gate_xnor = _make_binary('xnor', "Homomorphic bootstrapped XNOR gate.")
+gate_nor = _make_binary('nor', "Homomorphic bootstrapped NOR gate.")
+gate_andny = _make_binary('andny', "Homomorphic bootstrapped ANDNY (``(not a) and b``) gate.")
+gate_andyn = _make_binary('andyn', "Homomorphic bootstrapped ANDYN (``a and (not b)``) gate.")
+gate_orny = _make_binary('orny', "Homomorphic bootstrapped ORNY (``(not a) or b``) gate.")
+gate_oryn = _make_binary('oryn', "Homomorphic bootstrapped ORYN (``a or (not b)``) gate.")
+
+
+def gate_not(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, perf_params=None):
+    """Homomorphic NOT gate (does not need to be bootstrapped); gates.py:292-317."""
+    check_shape(result, a)
+    lwe_negate(thr, result, a)
+
+
+def gate_copy(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, perf_params=None):
+    """Homomorphic COPY gate (does not need to be bootstrapped); gates.py:320-345."""
+    check_shape(result, a)
+    lwe_copy(thr, result, a)
+
+
+def gate_constant(thr, cloud_key, result: LweSampleArray, vals, perf_params=None):
+    """Homomorphic CONSTANT gate: trivial encryptions of the given bits; gates.py:348-387."""
+    import torch
+    vals = numpy.asarray(vals)
+    if len(vals.shape) > len(result.shape) or vals.shape != tuple(result.shape[len(result.shape) - len(vals.shape):]):
+        raise ValueError(
+            ("The shape of the values {vshape} cannot be broadcasted to the shape "
+             "of the destination {dest_shape}").format(vshape=vals.shape, dest_shape=tuple(result.shape)))
+    mus = numpy.where(vals.astype(bool), MU, -MU).astype(numpy.int32)
+    lwe_noiseless_trivial(thr, result, thr.to_device(numpy.ascontiguousarray(mus)))
+
+
+def gate_mux(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, b: LweSampleArray,
+             c: LweSampleArray, perf_params=None):
+    """Homomorphic bootstrapped MUX (``b if a else c``) gate; gates.py:600-664.
+    Two blind rotations without key switch, then ONE key switch of ``(0,1/8) + u1 + u2`` with the
+    sum folded into the key-switch kernel's load."""
+    check_shape(result, a, b, c)
+    bk, ks = cloud_key.bootstrap_key, cloud_key.keyswitch_key
+    extracted_params = cloud_key.params.tgsw_params.tlwe_params.extracted_lweparams
+    u1 = LweSampleArray.empty(thr, extracted_params, result.shape)
+    u2 = LweSampleArray.empty(thr, extracted_params, result.shape)
+    and_const = phase_to_t32(-1, 8)
+    bootstrap_affine(thr, u1, bk, ks, MU, a, b, and_const, 1, 1, no_keyswitch=True)     # AND(a, b)
+    bootstrap_affine(thr, u2, bk, ks, MU, a, c, and_const, -1, 1, no_keyswitch=True)    # AND(not a, c)
+    _keyswitch_into(thr, result, ks, u1, u2, phase_to_t32(1, 8))

@@ -1,0 +1,182 @@
+"""The nufhe-compatible Python surface on the GPU: seeded keys equal the reference's (through the
+oracle, itself pinned to the reference), gates decrypt to truth tables, broadcasting / views /
+serialization / error behaviour follow test/test_api_high_level.py, test_api_low_level.py and
+test_gates.py of the reference."""
+import io
+
+import numpy
+import pytest
+import torch
+
+import gen_inputs as G
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nufhe():
+    import nufhe_b200
+    return nufhe_b200
+
+
+@pytest.fixture(scope='module')
+def ctx(nufhe):
+    return nufhe.Context(rng=nufhe.DeterministicRNG(G.GATE_SEED))
+
+
+@pytest.fixture(scope='module')
+def key_pair(ctx):
+    return ctx.make_key_pair()
+
+
+@pytest.fixture(scope='module')
+def okeys():
+    return O.OracleKeys(G.GATE_SEED)
+
+
+def host(t, unsigned=False):
+    a = t.cpu().numpy()
+    return a.view(numpy.uint64) if unsigned else a
+
+
+def test_seeded_keys_equal_reference_keys(key_pair, okeys):
+    sk, ck = key_pair
+    assert (host(sk.lwe_key.key) == okeys.lwe_key).all()
+    assert (host(ck.bootstrap_key.tgsw.samples.a.coeffs, True) == okeys.bk).all()
+    ks = ck.keyswitch_key.lwe
+    assert (host(ks.a) == okeys.ks_a).all() and (host(ks.b) == okeys.ks_b).all()
+    assert numpy.allclose(host(ks.current_variances), okeys.ks_cv)
+
+
+def test_encrypt_gate_decrypt_bit_exact(ctx, key_pair, okeys, nufhe):
+    sk, ck = key_pair
+    vm = ctx.make_virtual_machine(ck)
+    c1, c2 = ctx.encrypt(sk, G.GATE_BITS_A), ctx.encrypt(sk, G.GATE_BITS_B)
+    o1, o2 = okeys.encrypt(G.GATE_BITS_A), okeys.encrypt(G.GATE_BITS_B)
+    assert (host(c1.a) == o1[0]).all() and (host(c1.b) == o1[1]).all()
+    assert (host(c2.a) == o2[0]).all() and (host(c2.b) == o2[1]).all()
+    r = vm.gate_nand(c1, c2)
+    want = O.gate_binary('nand', o1, o2, okeys.bk, okeys.ks)
+    assert (host(r.a) == want[0]).all() and (host(r.b) == want[1]).all()
+    assert (ctx.decrypt(sk, r) == ~(numpy.array(G.GATE_BITS_A) & numpy.array(G.GATE_BITS_B))).all()
+
+
+ALL_BINARY = ['nand', 'or', 'and', 'xor', 'xnor', 'nor', 'andny', 'andyn', 'orny', 'oryn']
+
+
+def truth(name, a, b):
+    return dict(nand=~(a & b), xor=a ^ b, xnor=~(a ^ b), nor=~(a | b), andny=~a & b, andyn=a & ~b,
+                orny=~a | b, oryn=a | ~b, **{'or': a | b, 'and': a & b})[name]
+
+
+@pytest.mark.parametrize('name', ALL_BINARY)
+def test_binary_gate_truth_tables(ctx, key_pair, name):
+    sk, ck = key_pair
+    vm = ctx.make_virtual_machine(ck)
+    rng = numpy.random.RandomState(3)
+    a, b = rng.randint(0, 2, 32).astype(bool), rng.randint(0, 2, 32).astype(bool)
+    r = getattr(vm, 'gate_' + name)(ctx.encrypt(sk, a), ctx.encrypt(sk, b))
+    assert (ctx.decrypt(sk, r) == truth(name, a, b)).all()
+
+
+def test_mux_not_copy_constant(ctx, key_pair):
+    sk, ck = key_pair
+    vm = ctx.make_virtual_machine(ck)
+    rng = numpy.random.RandomState(4)
+    a, b, c = (rng.randint(0, 2, (2, 8)).astype(bool) for _ in range(3))
+    ca, cb, cc = ctx.encrypt(sk, a), ctx.encrypt(sk, b), ctx.encrypt(sk, c)
+    assert (ctx.decrypt(sk, vm.gate_mux(ca, cb, cc)) == numpy.where(a, b, c)).all()
+    assert (ctx.decrypt(sk, vm.gate_not(ca)) == ~a).all()
+    assert (ctx.decrypt(sk, vm.gate_copy(ca)) == a).all()
+    dest = vm.empty_ciphertext((2, 8))
+    vm.gate_constant(c[1].tolist(), dest=dest)
+    assert (ctx.decrypt(sk, dest) == numpy.broadcast_to(c[1], (2, 8))).all()
+
+
+def test_broadcasting_views_and_dest(ctx, key_pair):
+    sk, ck = key_pair
+    vm = ctx.make_virtual_machine(ck)
+    rng = numpy.random.RandomState(5)
+    a, b = rng.randint(0, 2, (3, 1)).astype(bool), rng.randint(0, 2, (4,)).astype(bool)
+    r = vm.gate_and(ctx.encrypt(sk, a), ctx.encrypt(sk, b))
+    assert r.shape == (3, 4) and (ctx.decrypt(sk, r) == (a & b)).all()
+    # strided views as inputs and as output (test_gates.py:514-559)
+    x, y = rng.randint(0, 2, (4, 6)).astype(bool), rng.randint(0, 2, (4, 6)).astype(bool)
+    cx, cy = ctx.encrypt(sk, x), ctx.encrypt(sk, y)
+    dest = vm.empty_ciphertext((4, 6))
+    vm.gate_constant(numpy.zeros((4, 6), bool), dest=dest)
+    vm.gate_xor(cx[1:3, ::2], cy[1:3, ::2], dest=dest[1:3, ::2])
+    got = ctx.decrypt(sk, dest)
+    want = numpy.zeros((4, 6), bool)
+    want[1:3, ::2] = x[1:3, ::2] ^ y[1:3, ::2]
+    assert (got == want).all()
+    # roll / concatenate / setitem / copy
+    import nufhe_b200 as nufhe
+    cat = nufhe.concatenate([cx, cy], axis=1)
+    assert cat.shape == (4, 12) and (ctx.decrypt(sk, cat) == numpy.concatenate([x, y], axis=1)).all()
+    cz = cx.copy()
+    cz.roll(2, axis=-1)
+    assert (ctx.decrypt(sk, cz) == numpy.roll(x, 2, axis=-1)).all()
+    cz[0] = cy[3]
+    assert (ctx.decrypt(sk, cz)[0] == y[3]).all()
+    with pytest.raises(ValueError):
+        cz[0] = 5
+
+
+def test_errors(ctx, key_pair, nufhe):
+    sk, ck = key_pair
+    vm = ctx.make_virtual_machine(ck)
+    c3, c4 = ctx.encrypt(sk, [1, 0, 1]), ctx.encrypt(sk, [1, 0, 1, 1])
+    with pytest.raises(ValueError):
+        vm.gate_nand(c3, c4)
+    with pytest.raises(ValueError):
+        vm.gate_nand(c3, c3, dest=vm.empty_ciphertext((2,)))
+    with pytest.raises(AttributeError):
+        vm.nand
+    with pytest.raises(ValueError):
+        nufhe.Context(api='OpenCL')
+
+
+def test_serialization_roundtrip(ctx, key_pair, nufhe):
+    sk, ck = key_pair
+    sk2 = ctx.load_secret_key(sk.dumps())
+    assert sk2 == sk
+    ct = ctx.encrypt(sk, [1, 0, 0, 1])
+    ct2 = ctx.load_ciphertext(ct.dumps())
+    assert ct2 == ct
+    f = io.BytesIO()
+    ck.dump(f)
+    f.seek(0)
+    ck2 = ctx.load_cloud_key(f)
+    assert ck2 == ck
+    vm = ctx.make_virtual_machine(ck2)
+    assert (ctx.decrypt(sk2, vm.gate_or(ct2, ct2)) == [True, False, False, True]).all()
+
+
+def test_low_level_api(key_pair, okeys, nufhe):
+    from nufhe_b200.engine import Engine
+    thr = Engine(0)
+    rng = nufhe.DeterministicRNG(G.GATE_SEED)
+    sk, ck = nufhe.make_key_pair(thr, rng)
+    assert (host(sk.lwe_key.key) == okeys.lwe_key).all()
+    ct = nufhe.encrypt(thr, rng, sk, [True, False])
+    res = nufhe.empty_ciphertext(thr, ck.params, (2,))
+    nufhe.gate_nand(thr, ck, res, ct, ct)
+    assert (nufhe.decrypt(thr, sk, res) == [False, True]).all()
+    # bootstrap seam (bootstrap.py:206-209) incl. no_keyswitch, and the explicit blind-rotate seam
+    from nufhe_b200.bootstrap import bootstrap
+    from nufhe_b200.lwe import LweSampleArray
+    ext = LweSampleArray.empty(thr, ck.params.tgsw_params.tlwe_params.extracted_lweparams, (2,))
+    bootstrap(thr, ext, ck.bootstrap_key, ck.keyswitch_key, 2**29, ct, no_keyswitch=True)
+    want = O.bootstrap(host(ct.a), host(ct.b), okeys.bk, None)
+    assert (host(ext.a) == want[0]).all() and (host(ext.b) == want[1]).all()
+
+
+def test_find_devices(nufhe):
+    devs = nufhe.find_devices()
+    assert len(devs) >= 1 and devs[0].api_name == 'CUDA'
+    import pickle
+    d = pickle.loads(pickle.dumps(devs[0]))
+    c = nufhe.Context(device_id=d)
+    assert c.thread.device.index == d.device_id

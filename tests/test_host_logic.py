@@ -1,0 +1,162 @@
+"""CPU-only tests: host logic of the nufhe-compatible API, the C ABI surface, and the host emulation
+of the per-lane GPU transform code against the oracle."""
+import ctypes
+import os
+import re
+
+import numpy
+import pytest
+
+import gen_inputs as G
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_capi_library_loads_and_exports_every_declared_symbol():
+    from nufhe_b200 import _native
+    lib = _native.load()
+    hdr = open(os.path.join(ROOT, 'include', 'nufhe_b200.h')).read()
+    declared = set(re.findall(r'\b(nb_[a-z0-9_]+)\s*\(', hdr)) - {'nb_ctx'}
+    assert declared == set(_native.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_capi_rejects_null_context_without_gpu():
+    from nufhe_b200 import _native
+    lib = _native.load()
+    assert lib.nb_ctx_synchronize(None) == _native.NB_EINVAL
+    assert lib.nb_ntt_forward_i32(None, None, None, 4) == _native.NB_EINVAL
+
+
+def test_engine_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from nufhe_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine()
+    import nufhe_b200 as nufhe
+    with pytest.raises(RuntimeError):
+        nufhe.Context()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'nufhe_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f
+                assert 'libnufhe_oracle' not in src, f
+
+
+def test_parameters_and_shapes():
+    import nufhe_b200 as nufhe
+    from nufhe_b200.gates import result_shape, check_shape
+    p = nufhe.NuFHEParameters()
+    assert p == nufhe.NuFHEParameters() and hash(p) == hash(nufhe.NuFHEParameters())
+    assert p.in_out_params.size == 500 and p.tgsw_params.tlwe_params.polynomial_degree == 1024
+    assert int(p.tgsw_params.offset) == -2145386496
+    assert p.ks_decomp_length == 8 and p.ks_log2_base == 2
+    with pytest.raises(ValueError):
+        nufhe.NuFHEParameters(transform_type='FFT')
+    with pytest.raises(ValueError):
+        nufhe.NuFHEParameters(tlwe_mask_size=2)
+    with pytest.raises(AssertionError):
+        nufhe.NuFHEParameters(transform_type='DCT')
+    pp = nufhe.PerformanceParameters(p, single_kernel_bootstrap=True)
+    assert pp == nufhe.PerformanceParameters(p, single_kernel_bootstrap=True)
+    assert pp != nufhe.PerformanceParameters(p)
+    with pytest.raises(AssertionError):
+        nufhe.PerformanceParameters(p, ntt_base_method='fortran')
+    # broadcasting rules of gates.py:51-78
+    assert result_shape((3, 1), (4,)) == (3, 4)
+    assert result_shape((2, 3), (1, 3), (3,)) == (2, 3)
+    with pytest.raises(ValueError):
+        result_shape((2, 3), (4, 3))
+
+    class S:
+        def __init__(self, shape):
+            self.shape = shape
+    check_shape(S((5, 2, 3)), S((2, 3)), S((3,)))
+    with pytest.raises(ValueError):
+        check_shape(S((2, 3)), S((5, 2, 3)))
+    with pytest.raises(ValueError):
+        check_shape(S((2, 4)), S((2, 3)))
+
+
+def test_encodings():
+    from nufhe_b200.numeric_functions import phase_to_t32, double_to_t32
+    from nufhe_b200.api_low_level import bool_to_t32, t32_to_bool
+    assert int(phase_to_t32(1, 8)) == 2**29 and int(phase_to_t32(-1, 8)) == -2**29
+    assert int(phase_to_t32(1, 4)) == 2**30 and int(phase_to_t32(-1, 4)) == -2**30
+    assert (bool_to_t32([True, False]) == [2**29, -2**29]).all()
+    assert (t32_to_bool(numpy.array([5, -5, 0])) == [True, False, False]).all()
+    assert (double_to_t32(numpy.array([0.25, -0.25, 1.25])) == [2**30, -2**30, 2**30]).all()
+
+
+def test_rng_matches_reference_semantics():
+    import nufhe_b200 as nufhe
+    r1, r2 = nufhe.DeterministicRNG(5), numpy.random.RandomState(5)
+    assert (r1.uniform_bool((7,)) == r2.randint(0, 2, size=(7,), dtype=numpy.int32)).all()
+    assert (r1.uniform_torus32((3, 2)) == r2.randint(-2**31, 2**31, size=(3, 2), dtype=numpy.int32)).all()
+    assert (r1.gauss((4,), 0.5) == r2.normal(size=(4,), scale=0.5)).all()
+    s = nufhe.SecureRNG()
+    assert s.uniform_bool((3, 5)).shape == (3, 5) and set(numpy.unique(s.uniform_bool((64,)))) <= {0, 1}
+    assert s.uniform_torus32((9,)).dtype == numpy.int32
+    g = s.gauss((1001,), 2.0)
+    assert g.shape == (1001,) and 1.0 < g.std() < 3.0
+
+
+# ---- the per-lane GPU transform code, executed on the host (csrc/host_emul.cpp) ------------------
+
+@pytest.fixture(scope='module')
+def emul():
+    path = os.path.join(ROOT, 'nufhe_b200', 'csrc', 'libnb_host_emul.so')
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+        g.build()
+    return ctypes.CDLL(path)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_lane_ntt_matches_oracle(emul):
+    rng = G.rs(5)
+    x = G.ff_numbers(rng, (3, 1024))
+    out = numpy.empty_like(x)
+    emul.emul_ntt_forward(_p(x), _p(out), ctypes.c_size_t(3))
+    assert (out == O.ntt_forward_u64(x)).all()
+    emul.emul_ntt_inverse(_p(x), _p(out), ctypes.c_size_t(3))
+    assert (out == O.ntt_inverse_u64(x)).all()
+
+
+def test_lane_ntt_matches_reference_golden(emul, golden):
+    g = golden('ntt')
+    _, x_u64 = G.ntt_inputs()
+    out = numpy.empty_like(x_u64)
+    emul.emul_ntt_forward(_p(x_u64), _p(out), ctypes.c_size_t(x_u64.shape[0]))
+    assert (out == g['fwd_u64']).all()
+    emul.emul_ntt_inverse(_p(x_u64), _p(out), ctypes.c_size_t(x_u64.shape[0]))
+    assert (out == g['inv_u64']).all()
+
+
+def test_lane_field_ops_match_oracle(emul, golden):
+    g = golden('arithmetic')
+    a, b, s = G.arithmetic_inputs()
+    a, b = a % numpy.uint64(G.P), b % numpy.uint64(G.P)
+    out = numpy.empty_like(a)
+    n = ctypes.c_size_t(a.size)
+    emul.emul_ff_mul(_p(a), _p(b), _p(out), n)
+    assert (out == g['mul']).all()
+    emul.emul_ff_add(_p(a), _p(b), _p(out), n)
+    assert (out == g['add']).all()
+    emul.emul_ff_sub(_p(a), _p(b), _p(out), n)
+    assert (out == g['sub']).all()
+    si = s.astype(numpy.int32)
+    emul.emul_ff_shl_var(_p(a), _p(si), _p(out), n)
+    assert (out == g['lsh']).all()
