@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libnufhe_b200.so')
+# NUFHE_B200_LIB lets a developer point at an experimental build of the same ABI (tools/ only)
+LIB_PATH = os.environ.get('NUFHE_B200_LIB') or os.path.join(_HERE, 'csrc', 'libnufhe_b200.so')
 
 NB_OK, NB_EINVAL, NB_EUNSUPPORTED, NB_ECUDA = 0, -1, -2, -3
 FF_ADD, FF_SUB, FF_MUL, FF_MUL_PREPARED, FF_PREPARE, FF_LSH = range(6)

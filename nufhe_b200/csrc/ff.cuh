@@ -19,6 +19,17 @@
 #define NB_D inline
 #endif
 
+// NB_LOCKSTEP(): keeps the warps of a CTA within one instruction-cache window of each other.
+// The transform code is fully unrolled straight-line code far larger than the SM's instruction
+// cache; warps that drift apart each stream it from L2 on their own ("no instruction" stalls were
+// the top stall reason in the first ncu capture, profiles/r1_v1_*).  A cheap CTA barrier every few
+// hundred instructions makes one fetch serve all warps.
+#if defined(__CUDA_ARCH__) && defined(NB_LOCKSTEP_ON)
+#define NB_LOCKSTEP() __syncthreads()
+#else
+#define NB_LOCKSTEP() ((void)0)
+#endif
+
 namespace nb {
 
 typedef uint64_t u64;

@@ -60,17 +60,22 @@ __global__ void __launch_bounds__(128) ntt_forward_kernel(const void *__restrict
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 *scratch = scratch_all + warp * TR_WORDS;
-    for (size_t p = (size_t)blockIdx.x * 4 + warp; p < batch; p += (size_t)gridDim.x * 4) {
+    // every warp of the CTA runs the same number of iterations (NB_LOCKSTEP barriers inside)
+    for (size_t p0 = (size_t)blockIdx.x * 4; p0 < batch; p0 += (size_t)gridDim.x * 4) {
+        const size_t p = p0 + warp;
+        const bool live = p < batch;
         u64 v[32];
 #pragma unroll
         for (int s = 0; s < 32; s++) {
-            size_t idx = p * NTT_N + ntt_in_index(lane, s);
+            size_t idx = (live ? p : p0) * NTT_N + ntt_in_index(lane, s);
             if (IN_I32) v[s] = ff_from_i32(((const i32 *)in)[idx]);
             else v[s] = ff_canon(((const u64 *)in)[idx]);
         }
         warp_ntt_forward(v, scratch, twd, lane);
+        if (live) {
 #pragma unroll
-        for (int s = 0; s < 32; s++) out[p * NTT_N + ntt_out_index(lane, s)] = v[s];
+            for (int s = 0; s < 32; s++) out[p * NTT_N + ntt_out_index(lane, s)] = v[s];
+        }
     }
 }
 
@@ -84,16 +89,20 @@ __global__ void __launch_bounds__(128) ntt_inverse_kernel(const u64 *__restrict_
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 *scratch = scratch_all + warp * TR_WORDS;
-    for (size_t p = (size_t)blockIdx.x * 4 + warp; p < batch; p += (size_t)gridDim.x * 4) {
+    for (size_t p0 = (size_t)blockIdx.x * 4; p0 < batch; p0 += (size_t)gridDim.x * 4) {
+        const size_t p = p0 + warp;
+        const bool live = p < batch;
         u64 v[32];
 #pragma unroll
-        for (int s = 0; s < 32; s++) v[s] = ff_canon(in[p * NTT_N + ntt_out_index(lane, s)]);
+        for (int s = 0; s < 32; s++) v[s] = ff_canon(in[(live ? p : p0) * NTT_N + ntt_out_index(lane, s)]);
         warp_ntt_inverse(v, scratch, twd, lane);
+        if (live) {
 #pragma unroll
-        for (int s = 0; s < 32; s++) {
-            size_t idx = p * NTT_N + ntt_in_index(lane, s);
-            if (OUT_I32) ((i32 *)out)[idx] = ff_to_i32(v[s]);
-            else ((u64 *)out)[idx] = v[s];
+            for (int s = 0; s < 32; s++) {
+                size_t idx = p * NTT_N + ntt_in_index(lane, s);
+                if (OUT_I32) ((i32 *)out)[idx] = ff_to_i32(v[s]);
+                else ((u64 *)out)[idx] = v[s];
+            }
         }
     }
 }
@@ -194,6 +203,7 @@ NB_D void external_product_step(const WarpState &w, const u64 *__restrict__ bk_r
             v1[s] = ff_from_i32(d1);
         }
     }
+    NB_LOCKSTEP();
     // 2. forward transforms of the two digits
     warp_ntt_forward(v0, w.scratch, w.twd_fwd, lane);
     warp_ntt_forward(v1, w.scratch, w.twd_fwd, lane);
@@ -208,6 +218,7 @@ NB_D void external_product_step(const WarpState &w, const u64 *__restrict__ bk_r
             u64 p1 = ff_mul2_add(v0[t], b0.y, v1[t], b1.y);      // contribution to output polynomial 1
             v0[t] = w.mi ? p1 : p0;
             w.xchg_out[t * 32 + lane] = w.mi ? p0 : p1;
+            if (t % 4 == 3) NB_LOCKSTEP();
         }
     }
     pair_barrier(w.bar_id);

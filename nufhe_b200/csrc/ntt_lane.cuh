@@ -64,6 +64,7 @@ template <int LOGN, int ROOTLOG, int BASE> NB_HD void dif_inlane(u64 *v)
             v[i0] = ff_add(a, b);
             v[i1] = ff_shl<(ROOTLOG * k * (1 << s)) % 192>(ff_sub(a, b));
         });
+        NB_LOCKSTEP();
     });
 }
 
@@ -83,6 +84,7 @@ template <int LOGN, int ROOTLOG, int BASE> NB_HD void dit_inlane(u64 *v)
             v[i0] = ff_add(a, t);
             v[i1] = ff_sub(a, t);
         });
+        NB_LOCKSTEP();
     });
 }
 
@@ -102,6 +104,7 @@ NB_HD void ntt_fwd_pre(u64 *v, const u64 *twd, int lane)
     static_for<0, 32>([&](auto T) {
         constexpr int t = decltype(T)::value;
         v[t] = ff_mul(v[t], twd[t * 32]);
+        if (t % 16 == 15) NB_LOCKSTEP();
     });
     const int sh = 3 * lane;
     static_for<0, 16>([&](auto I) {
@@ -110,6 +113,7 @@ NB_HD void ntt_fwd_pre(u64 *v, const u64 *twd, int lane)
         v[i] = ff_add(a, b);
         v[16 + i] = ff_shl_var(ff_sub(a, b), sh);
     });
+    NB_LOCKSTEP();
 }
 // stage C1 (after the transpose)
 NB_HD void ntt_fwd_post(u64 *v) { dif_inlane<5, 6, 0>(v); }
@@ -127,9 +131,11 @@ NB_HD void ntt_inv_post(u64 *v, const u64 *twd_inv, int lane)
         v[i] = ff_add(a, t);
         v[16 + i] = ff_sub(a, t);
     });
+    NB_LOCKSTEP();
     static_for<0, 32>([&](auto T) {
         constexpr int t = decltype(T)::value;
         v[t] = ff_mul(v[t], twd_inv[t * 32]);
+        if (t % 16 == 15) NB_LOCKSTEP();
     });
     static_for<0, 2>([&](auto H) {
         constexpr int h = decltype(H)::value;
