@@ -1,0 +1,310 @@
+// br_phases.cuh -- the bootstrap step as CTA-wide phases over shared-memory-resident polynomials.
+//
+// Why: the first version kept a whole polynomial in one warp's registers (32 elements per lane) and was
+// limited by instruction supply (profiles/r1_v1_analysis.md).  Here every phase is executed by all
+// threads of the CTA at the same time on 16 elements per thread, with 16 warps per SM, so that four warps
+// per scheduler share each fetched line and no thread needs more than 128 registers.
+//
+// A CTA of 512 threads owns CT = 4 ciphertexts.  Shared memory holds, per ciphertext, the accumulator
+// (2 x 1024 Torus32) and 4 work polynomials of 1024 field elements; a work polynomial is 16 rows of 64
+// columns (padded to 66) -- row r holds inner-transform output k1 = brev4(r), column = position along
+// the outer 64-point transform.  The transform is the factorisation of ntt_lane.cuh,
+//     X[k1 + 16 k2] = sum_j2 w64^(j2 k2) psi^(j2 (2 k1 + 1)) sum_j1 x[64 j1 + j2] w32^(j1 (2 k1 + 1)),
+// computed in three in-place passes:
+//     fwd1: 16-point transform over j1 (stride 64) + the psi twiddle       task = (poly, j2)
+//     fwd2: first two layers of the 64-point transform (radix 4 over a = j2 / 16) and the 2^(3 b kappa)
+//           twiddle, b = j2 % 16                                            task = (poly, row, g = b / 4)
+//     fwd3: 16-point transform over b                                       task = (poly, row, u)
+// The inverse runs the mirrored passes inv3, inv2, inv1.  Between fwd3 and inv3 the multiply-accumulate
+// with the bootstrap-key row works point-wise on pairs of adjacent columns.
+//
+// Column c = 16 a + b of a row is stored at 16 a + swz(a, b) (an XOR on the pair index) so that the
+// 128-bit accesses of fwd2/fwd3/inv3/inv2 are bank-conflict free; see the derivation in DESIGN.md.
+//
+// All functions are __host__ __device__: csrc/host_emul.cpp runs them phase by phase on the CPU (a
+// barrier between phases), which lets the CPU-only test-suite check every index map against the oracle.
+#pragma once
+#include "ntt_lane.cuh"
+
+namespace nb {
+
+constexpr int BR2_CT = 4;                         // ciphertexts per CTA
+constexpr int BR2_THREADS = 512;
+constexpr int ROW_STRIDE = 66;                    // u64 per row (64 + 2 padding)
+constexpr int POLY_STRIDE = 16 * ROW_STRIDE;      // u64 per work polynomial
+constexpr int BR2_POLYS = 4 * BR2_CT;             // work polynomials per CTA
+
+// 16-byte accesses to two adjacent field elements (shared memory rows and key rows are 16-byte aligned)
+NB_HD void ld2(const u64 *p, u64 &x, u64 &y)
+{
+#if defined(__CUDA_ARCH__)
+    ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p);
+    x = t.x; y = t.y;
+#else
+    x = p[0]; y = p[1];
+#endif
+}
+NB_HD void ld2_global(const u64 *p, u64 &x, u64 &y)
+{
+#if defined(__CUDA_ARCH__)
+    ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    x = t.x; y = t.y;
+#else
+    x = p[0]; y = p[1];
+#endif
+}
+NB_HD void st2(u64 *p, u64 x, u64 y)
+{
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(x, y);
+#else
+    p[0] = x; p[1] = y;
+#endif
+}
+
+// stored column of logical column (a, b): pair index XOR 2a
+NB_HD int swz(int a, int b) { return ((((b >> 1) ^ (2 * a)) & 7) << 1) | (b & 1); }
+NB_HD int col_of(int a, int b) { return 16 * a + swz(a, b); }
+
+// natural NTT index of the transformed element stored at (row, stored column)
+NB_HD int w_natural_index(int row, int scol)
+{
+    int u = scol >> 4, sb = scol & 15;
+    int i = ((((sb >> 1) ^ (2 * u)) & 7) << 1) | (sb & 1);
+    int k1 = brev(row, 4), k2 = brev(u, 2) + 4 * brev(i, 4);
+    return k1 + 16 * k2;
+}
+// twiddle exponent (power of psi) applied by fwd1 to (row, j2)
+NB_HD int w_twiddle_exponent(int row, int j2) { return (j2 * (2 * brev(row, 4) + 1)) % 2048; }
+
+// gadget decomposition digit j of one coefficient (tgsw_gpu.py:31-54; blind_rotate.mako:41-43,116-124)
+NB_HD i32 decomp_digit(i32 c, int j)
+{
+    const u32 offset = 0x80000000u + (1u << 21);
+    i32 t = (i32)((u32)c + offset);
+    return ((t >> (22 - 10 * j)) & 1023) - 512;
+}
+
+// (X^a - 1) * acc at index idx  (polynomials_gpu.mako:18-77 with minus_one; blind_rotate.mako:100-114)
+NB_HD i32 rotate_minus_one(const i32 *acc, int idx, int ar, bool flip)
+{
+    i32 src = acc[(idx - ar) & (NTT_N - 1)];
+    bool neg = (idx < ar) != flip;
+    return (i32)((neg ? 0u - (u32)src : (u32)src) - (u32)acc[idx]);
+}
+
+// ---- fwd1: task = (poly p, j2); reads ACC, writes W[p][row][col(j2)] -------------------------------
+// twd: forward table [row][j2] (64 per row).  ROTATE=false: digits of acc itself (plain external product).
+template <bool ROTATE>
+NB_HD void phase_fwd1(int task, const i32 *acc_all, u64 *w_all, const u64 *twd, const int *rot_a)
+{
+    const int j2 = task & 63, p = task >> 6;           // p = ct * 4 + mi * 2 + j
+    const int ct = p >> 2, mi = (p >> 1) & 1, j = p & 1;
+    const i32 *acc = acc_all + (ct * 2 + mi) * NTT_N;
+    const int a = ROTATE ? rot_a[ct] : 0;
+    const int ar = a & (NTT_N - 1);
+    const bool flip = (a >> 10) & 1;
+    u64 v[16];
+    static_for<0, 16>([&](auto J) {
+        constexpr int j1 = decltype(J)::value;
+        const int idx = 64 * j1 + j2;
+        i32 c = ROTATE ? rotate_minus_one(acc, idx, ar, flip) : acc[idx];
+        v[j1] = ff_shl<6 * j1>(ff_from_i32(decomp_digit(c, j)));
+    });
+    dif_inlane<4, 12, 0>(v);
+    u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        w[r * ROW_STRIDE] = ff_mul(v[r], twd[r * 64 + j2]);
+    });
+}
+
+// ---- fwd2 / inv2: task = (poly p, row, g); 16 elements (a, e), b = 4 g + e ---------------------------
+template <int G> NB_HD void fwd2_twiddle(u64 *v)
+{
+    static_for<1, 4>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        constexpr int kappa = brev(u, 2);
+        static_for<0, 4>([&](auto E) {
+            constexpr int e = decltype(E)::value;
+            v[u * 4 + e] = ff_shl<(3 * kappa * (4 * G + e)) % 192>(v[u * 4 + e]);
+        });
+    });
+}
+template <int G> NB_HD void inv2_twiddle(u64 *v)
+{
+    static_for<1, 4>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        constexpr int kappa = brev(u, 2);
+        static_for<0, 4>([&](auto E) {
+            constexpr int e = decltype(E)::value;
+            v[u * 4 + e] = ff_shl<(192 - (3 * kappa * (4 * G + e)) % 192) % 192>(v[u * 4 + e]);
+        });
+    });
+}
+
+// col_of(a, 4 g + e) = 16 a + 4 (g ^ a) + e: the four e of a thread are contiguous (2 x 16 bytes)
+NB_HD void load16_ae(u64 *v, const u64 *row, int g)
+{
+    static_for<0, 4>([&](auto A) {
+        constexpr int a = decltype(A)::value;
+        const u64 *src = row + 16 * a + 4 * (g ^ a);
+        ld2(src, v[a * 4 + 0], v[a * 4 + 1]);
+        ld2(src + 2, v[a * 4 + 2], v[a * 4 + 3]);
+    });
+}
+NB_HD void store16_ae(const u64 *v, u64 *row, int g)
+{
+    static_for<0, 4>([&](auto A) {
+        constexpr int a = decltype(A)::value;
+        u64 *dst = row + 16 * a + 4 * (g ^ a);
+        st2(dst, v[a * 4 + 0], v[a * 4 + 1]);
+        st2(dst + 2, v[a * 4 + 2], v[a * 4 + 3]);
+    });
+}
+// the 16 logical columns of block u, pair pi stored at pair position pi ^ 2u
+NB_HD void load16_b(u64 *v, const u64 *row, int u)
+{
+    static_for<0, 8>([&](auto PI) {
+        constexpr int pi = decltype(PI)::value;
+        ld2(row + 16 * u + 2 * ((pi ^ (2 * u)) & 7), v[2 * pi], v[2 * pi + 1]);
+    });
+}
+NB_HD void store16_b(const u64 *v, u64 *row, int u)
+{
+    static_for<0, 8>([&](auto PI) {
+        constexpr int pi = decltype(PI)::value;
+        st2(row + 16 * u + 2 * ((pi ^ (2 * u)) & 7), v[2 * pi], v[2 * pi + 1]);
+    });
+}
+
+NB_HD void phase_fwd2(int p, int row, int g, u64 *w_all)
+{
+    u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[16];
+    load16_ae(v, w, g);
+    static_for<0, 4>([&](auto E) { dif_inlane<2, 48, decltype(E)::value, 4>(v); });
+    switch (g) {           // g is warp-uniform by construction of the task map
+    case 0: fwd2_twiddle<0>(v); break;
+    case 1: fwd2_twiddle<1>(v); break;
+    case 2: fwd2_twiddle<2>(v); break;
+    default: fwd2_twiddle<3>(v); break;
+    }
+    store16_ae(v, w, g);
+}
+
+NB_HD void phase_inv2(int p, int row, int g, u64 *w_all)
+{
+    u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[16];
+    load16_ae(v, w, g);
+    switch (g) {
+    case 0: inv2_twiddle<0>(v); break;
+    case 1: inv2_twiddle<1>(v); break;
+    case 2: inv2_twiddle<2>(v); break;
+    default: inv2_twiddle<3>(v); break;
+    }
+    static_for<0, 4>([&](auto E) { dit_inlane<2, 48, decltype(E)::value, 4>(v); });
+    store16_ae(v, w, g);
+}
+
+// ---- fwd3 / inv3: task = (poly p, row, u): the 16 logical columns b of block u ---------------------
+NB_HD void phase_fwd3(int p, int row, int u, u64 *w_all)
+{
+    u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[16];
+    load16_b(v, w, u);
+    dif_inlane<4, 12, 0>(v);
+    store16_b(v, w, u);
+}
+NB_HD void phase_inv3(int p, int row, int u, u64 *w_all)
+{
+    u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[16];
+    load16_b(v, w, u);
+    dit_inlane<4, 12, 0>(v);
+    store16_b(v, w, u);
+}
+
+// ---- MAC: thread = (row, pair q): stored columns 2q, 2q+1 of every work polynomial -----------------
+// bk_row: internal layout [mi][j][mo][row * 64 + stored column], plain (non-Montgomery) values.
+// out polynomial mo of ciphertext ct overwrites work polynomial ct*4 + mo.
+NB_HD void phase_mac(int row, int q, u64 *w_all, const u64 *bk_row)
+{
+    const int pos = row * 64 + 2 * q;
+    u64 bk[8][2];
+    static_for<0, 8>([&](auto M) {
+        constexpr int m = decltype(M)::value;            // m = (mi * 2 + j) * 2 + mo
+        ld2_global(bk_row + m * NTT_N + pos, bk[m][0], bk[m][1]);
+    });
+    for (int ct = 0; ct < BR2_CT; ct++) {
+        u64 *w = w_all + ct * 4 * POLY_STRIDE + row * ROW_STRIDE + 2 * q;
+        u64 f[4][2];
+        static_for<0, 4>([&](auto D) {
+            constexpr int d = decltype(D)::value;        // d = mi * 2 + j
+            ld2(w + d * POLY_STRIDE, f[d][0], f[d][1]);
+        });
+        static_for<0, 2>([&](auto MO) {
+            constexpr int mo = decltype(MO)::value;
+            u64 o[2];
+            static_for<0, 2>([&](auto X) {
+                constexpr int x = decltype(X)::value;
+                u64 s = ff_mul2_add(f[0][x], bk[0 * 2 + mo][x], f[1][x], bk[1 * 2 + mo][x]);
+                u64 t = ff_mul2_add(f[2][x], bk[2 * 2 + mo][x], f[3][x], bk[3 * 2 + mo][x]);
+                o[x] = ff_add(s, t);
+            });
+            st2(w + mo * POLY_STRIDE, o[0], o[1]);
+        });
+    }
+}
+
+// ---- inv1: task = (ct, mo, j2): reads W[ct*4+mo], writes ACC[ct][mo] --------------------------------
+// twd_inv: [row][j2] = psi^-(j2 (2 k1 + 1)) / 1024.  ACCUMULATE: acc += result, else acc = result.
+template <bool ACCUMULATE>
+NB_HD void phase_inv1(int task, i32 *acc_all, const u64 *w_all, const u64 *twd_inv)
+{
+    const int j2 = task & 63, pp = task >> 6;          // pp = ct * 2 + mo
+    const int ct = pp >> 1, mo = pp & 1;
+    const u64 *w = w_all + (ct * 4 + mo) * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
+    u64 v[16];
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        v[r] = ff_mul(w[r * ROW_STRIDE], twd_inv[r * 64 + j2]);
+    });
+    dit_inlane<4, 12, 0>(v);
+    i32 *acc = acc_all + (ct * 2 + mo) * NTT_N;
+    static_for<0, 16>([&](auto J) {
+        constexpr int j1 = decltype(J)::value;
+        const int idx = 64 * j1 + j2;
+        i32 r = ff_to_i32(ff_shl<(192 - 6 * j1) % 192>(v[j1]));
+        acc[idx] = ACCUMULATE ? (i32)((u32)acc[idx] + (u32)r) : r;
+    });
+}
+
+// thread -> task maps (tid in [0, 512), it = iteration)
+NB_HD void map_fwd2(int tid, int it, int &p, int &row, int &g)
+{
+    g = tid >> 7;                                      // warp-uniform
+    int x = it * 128 + (tid & 127);
+    p = x >> 4; row = x & 15;
+}
+NB_HD void map_fwd3(int tid, int it, int &p, int &row, int &u)
+{
+    u = tid & 3; row = (tid >> 2) & 15; p = it * 8 + (tid >> 6);
+}
+// inverse passes act on polynomials ct*4 + mo only (8 of the 16)
+NB_HD void map_inv2(int tid, int &p, int &row, int &g)
+{
+    g = tid >> 7;
+    int x = tid & 127;                                 // 8 polys x 16 rows
+    int pp = x >> 4; row = x & 15;
+    p = (pp >> 1) * 4 + (pp & 1);
+}
+NB_HD void map_inv3(int tid, int &p, int &row, int &u)
+{
+    u = tid & 3; row = (tid >> 2) & 15;
+    int pp = tid >> 6;
+    p = (pp >> 1) * 4 + (pp & 1);
+}
+
+}  // namespace nb

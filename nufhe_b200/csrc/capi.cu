@@ -11,7 +11,8 @@ using namespace nb;
 struct nb_ctx {
     int device;
     cudaStream_t stream;
-    u64 *d_twd_fwd, *d_twd_inv;
+    u64 *d_twd_fwd, *d_twd_inv;          // warp-NTT tables (stand-alone transforms)
+    u64 *d_ph_fwd, *d_ph_inv;            // phase tables (fused bootstrap)
     int sm_count;
     std::string err;
 };
@@ -45,7 +46,7 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     nb_ctx *ctx = new nb_ctx();
     ctx->device = device;
     ctx->stream = (cudaStream_t)stream;
-    ctx->d_twd_fwd = ctx->d_twd_inv = nullptr;
+    ctx->d_twd_fwd = ctx->d_twd_inv = ctx->d_ph_fwd = ctx->d_ph_inv = nullptr;
     *out = ctx;   // returned even on failure so that nb_last_error() can be read; caller destroys it
     NB_TRY(check(ctx, cudaSetDevice(device), "cudaSetDevice"));
     cudaDeviceProp prop;
@@ -59,10 +60,13 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     NB_TRY(check(ctx, cudaMalloc(&ctx->d_twd_inv, NTT_N * sizeof(u64)), "cudaMalloc"));
     NB_TRY(check(ctx, cudaMemcpy(ctx->d_twd_fwd, t.fwd.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
     NB_TRY(check(ctx, cudaMemcpy(ctx->d_twd_inv, t.inv.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
+    PhaseTables pt;
+    NB_TRY(check(ctx, cudaMalloc(&ctx->d_ph_fwd, NTT_N * sizeof(u64)), "cudaMalloc"));
+    NB_TRY(check(ctx, cudaMalloc(&ctx->d_ph_inv, NTT_N * sizeof(u64)), "cudaMalloc"));
+    NB_TRY(check(ctx, cudaMemcpy(ctx->d_ph_fwd, pt.fwd.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
+    NB_TRY(check(ctx, cudaMemcpy(ctx->d_ph_inv, pt.inv.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)BR_SMEM_BYTES), "cudaFuncSetAttribute(blind_rotate)"));
-    NB_TRY(check(ctx, cudaFuncSetAttribute(external_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)BR_SMEM_BYTES), "cudaFuncSetAttribute(external_product)"));
+                                           (int)BR2_SMEM_BYTES), "cudaFuncSetAttribute(blind_rotate)"));
     return NB_OK;
 }
 
@@ -72,6 +76,8 @@ void nb_ctx_destroy(nb_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->d_twd_fwd) cudaFree(ctx->d_twd_fwd);
     if (ctx->d_twd_inv) cudaFree(ctx->d_twd_inv);
+    if (ctx->d_ph_fwd) cudaFree(ctx->d_ph_fwd);
+    if (ctx->d_ph_inv) cudaFree(ctx->d_ph_inv);
     delete ctx;
 }
 
@@ -103,7 +109,7 @@ const char *nb_build_info(void)
         snprintf(buf, sizeof(buf),
                  "nufhe_b200 sm_100a; blind_rotate: %d regs, %zu B dyn smem, %d thr/CTA, %d ct/CTA; "
                  "ntt_forward: %d regs; keyswitch: %d regs, tile %d",
-                 a.numRegs, BR_SMEM_BYTES, BR_THREADS, BR_CT_PER_CTA, b.numRegs, c.numRegs, KS_TILE);
+                 a.numRegs, BR2_SMEM_BYTES, BR2_THREADS, BR2_CT, b.numRegs, c.numRegs, KS_TILE);
         info = buf;
     }
     return info.c_str();
@@ -185,10 +191,12 @@ int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, siz
     if (!ctx || !accum || !bk_int) return fail(ctx, NB_EINVAL, "nb_external_product: null argument");
     if (batch == 0) return NB_OK;
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
-    int grid = (int)((batch + BR_CT_PER_CTA - 1) / BR_CT_PER_CTA);
-    external_product_kernel<<<grid, BR_THREADS, BR_SMEM_BYTES, ctx->stream>>>(
-        accum, (const u64 *)bk_int + bk_row * 8 * NTT_N, batch, ctx->d_twd_fwd, ctx->d_twd_inv);
-    return launch_check(ctx, "external_product_kernel");
+    BlindRotateArgs p{};
+    p.accum = accum; p.accum_out = accum; p.bk = (const u64 *)bk_int + bk_row * 8 * NTT_N;
+    p.plain = 1; p.batch = batch;
+    int grid = (int)((batch + BR2_CT - 1) / BR2_CT);
+    blind_rotate_kernel<<<grid, BR2_THREADS, BR2_SMEM_BYTES, ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);
+    return launch_check(ctx, "blind_rotate_kernel(plain external product)");
 }
 
 static int launch_blind_rotate(nb_ctx *ctx, BlindRotateArgs &p)
@@ -196,8 +204,8 @@ static int launch_blind_rotate(nb_ctx *ctx, BlindRotateArgs &p)
     if (p.n <= 0 || p.n > LWE_N_MAX) return fail(ctx, NB_EUNSUPPORTED, "LWE dimension out of range");
     if (p.batch == 0) return NB_OK;
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
-    int grid = (int)((p.batch + BR_CT_PER_CTA - 1) / BR_CT_PER_CTA);
-    blind_rotate_kernel<<<grid, BR_THREADS, BR_SMEM_BYTES, ctx->stream>>>(p, ctx->d_twd_fwd, ctx->d_twd_inv);
+    int grid = (int)((p.batch + BR2_CT - 1) / BR2_CT);
+    blind_rotate_kernel<<<grid, BR2_THREADS, BR2_SMEM_BYTES, ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);
     return launch_check(ctx, "blind_rotate_kernel");
 }
 

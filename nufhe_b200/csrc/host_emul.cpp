@@ -4,6 +4,7 @@
 // index maps, twiddle tables and shift constants of the GPU transform against the oracle.
 // This is a test aid for the CUDA source, not a CPU fallback: nothing in nufhe_b200/ loads it.
 #include <cstring>
+#include <vector>
 #include "tables.h"
 
 using namespace nb;
@@ -51,6 +52,43 @@ void emul_ntt_inverse(const u64 *in, u64 *out, size_t batch)
             for (int s = 0; s < 32; s++) out[b * NTT_N + ntt_in_index(l, s)] = v[l][s];
         }
     }
+}
+
+// One external-product step of the phase-structured kernel (br_phases.cuh) for up to BR2_CT
+// ciphertexts, phases executed in order with all "threads" of a phase run back to back.
+// acc: (nct, 2, 1024) in/out; bk_ref_row: reference layout (2,2,2,1024) Montgomery; rot: rotation
+// amounts per ciphertext or NULL (plain external product, overwrite).
+void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct)
+{
+    static PhaseTables T;
+    std::vector<i32> acc(BR2_CT * 2 * NTT_N, 0);
+    std::vector<u64> w(BR2_POLYS * POLY_STRIDE, 0);
+    std::vector<u64> bk(8 * NTT_N);
+    for (int c = 0; c < nct; c++) memcpy(&acc[c * 2 * NTT_N], acc_io + c * 2 * NTT_N, sizeof(i32) * 2 * NTT_N);
+    int rots[BR2_CT] = {0, 0, 0, 0};
+    if (rot) for (int c = 0; c < nct; c++) rots[c] = rot[c];
+    // bk_prepare: internal [m][row*64 + scol] plain
+    for (int m = 0; m < 8; m++)
+        for (int row = 0; row < 16; row++)
+            for (int sc = 0; sc < 64; sc++)
+                bk[m * NTT_N + row * 64 + sc] = ff_mul(ff_canon(bk_ref_row[m * NTT_N + w_natural_index(row, sc)]), FF_RINV);
+    for (int it = 0; it < 2; it++)
+        for (int tid = 0; tid < BR2_THREADS; tid++) {
+            if (rot) phase_fwd1<true>(it * BR2_THREADS + tid, acc.data(), w.data(), T.fwd.data(), rots);
+            else phase_fwd1<false>(it * BR2_THREADS + tid, acc.data(), w.data(), T.fwd.data(), rots);
+        }
+    for (int it = 0; it < 2; it++)
+        for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, g; map_fwd2(tid, it, p, r, g); phase_fwd2(p, r, g, w.data()); }
+    for (int it = 0; it < 2; it++)
+        for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, u; map_fwd3(tid, it, p, r, u); phase_fwd3(p, r, u, w.data()); }
+    for (int tid = 0; tid < BR2_THREADS; tid++) phase_mac(tid >> 5, tid & 31, w.data(), bk.data());
+    for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, u; map_inv3(tid, p, r, u); phase_inv3(p, r, u, w.data()); }
+    for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, g; map_inv2(tid, p, r, g); phase_inv2(p, r, g, w.data()); }
+    for (int tid = 0; tid < BR2_THREADS; tid++) {
+        if (rot) phase_inv1<true>(tid, acc.data(), w.data(), T.inv.data());
+        else phase_inv1<false>(tid, acc.data(), w.data(), T.inv.data());
+    }
+    for (int c = 0; c < nct; c++) memcpy(acc_io + c * 2 * NTT_N, &acc[c * 2 * NTT_N], sizeof(i32) * 2 * NTT_N);
 }
 
 void emul_ff_shl_var(const u64 *in, const int *s, u64 *out, size_t n)

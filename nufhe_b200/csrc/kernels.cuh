@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "ntt_lane.cuh"
+#include "br_phases.cuh"
 
 namespace nb {
 
@@ -131,119 +132,29 @@ __global__ void ff_elementwise_kernel(int op, const u64 *__restrict__ a, const u
 
 // ---- bootstrap-key layout ------------------------------------------------------------------------
 // reference row (nufhe/blind_rotate.py:112): [mi][j][mo][k], values NTT(bk) * 2^64 (Montgomery form).
-// internal row: [mi][slot][j][lane][mo], plain values, so that in the MAC lane `lane` of warp `mi`
-// reads, for transform slot `slot` and digit j, one 16-byte pair (mo = 0, 1).
+// internal row: [m = (mi*2+j)*2+mo][row * 64 + stored column] (br_phases.cuh), plain values, so that the
+// MAC phase reads, per thread, one 16-byte pair from each of the 8 planes, coalesced across the CTA.
 __global__ void bk_prepare_kernel(const u64 *__restrict__ bk_ref, u64 *__restrict__ bk_int, size_t rows)
 {
     const size_t total = rows * 8 * NTT_N;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t row = i / (8 * NTT_N);
         int r = (int)(i % (8 * NTT_N));
-        int mo = r & 1, lane = (r >> 1) & 31, j = (r >> 6) & 1, slot = (r >> 7) & 31, mi = r >> 12;
-        int k = ntt_out_index(lane, slot);
-        u64 x = bk_ref[row * 8 * NTT_N + (((mi * 2 + j) * 2 + mo) * NTT_N + k)];
+        int m = r >> 10, pos = r & 1023;
+        int k = w_natural_index(pos >> 6, pos & 63);
+        u64 x = bk_ref[row * 8 * NTT_N + m * NTT_N + k];
         bk_int[i] = ff_mul(ff_canon(x), FF_RINV);
     }
-}
-
-// ---- the external-product step shared by the fused bootstrap and the stand-alone kernel ---------
-struct WarpState {
-    int lane;        // 0..31
-    int mi;          // which accumulator polynomial this warp owns (0: mask, 1: body)
-    int bar_id;      // named barrier shared with the partner warp
-    i32 *acc;        // this warp's polynomial, 1024 Torus32 in shared memory, natural order
-    u64 *scratch;    // transpose scratch, TR_WORDS
-    u64 *xchg_out;   // partial products this warp hands to its partner, [slot][lane]
-    u64 *xchg_in;    // the partner's buffer
-    const u64 *twd_fwd, *twd_inv;   // shared-memory tables [slot][lane]
-};
-
-NB_D void pair_barrier(int id)
-{
-#if defined(__CUDA_ARCH__)
-    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
-#endif
-}
-
-// gadget decomposition of one coefficient (tgsw_gpu.py:31-54; blind_rotate.mako:41-43,116-124)
-NB_D void decompose(i32 c, i32 &d0, i32 &d1)
-{
-    const u32 offset = 0x80000000u + (1u << 21);
-    i32 t = (i32)((u32)c + offset);
-    d0 = ((t >> 22) & 1023) - 512;
-    d1 = ((t >> 12) & 1023) - 512;
-}
-
-// ROTATE: acc += bk_row (x) ((X^a - 1) acc)      (mux_rotate, nufhe/bootstrap.py:96-109)
-// else  : acc  = bk_row (x) acc                  (tgsw_transformed_external_mul, tgsw.py:165-172)
-// bk_row: internal layout (bk_prepare_kernel), this kernel reads it through the read-only path.
-template <bool ROTATE>
-NB_D void external_product_step(const WarpState &w, const u64 *__restrict__ bk_row, int a)
-{
-    const int lane = w.lane;
-    u64 v0[32], v1[32];
-    // 1. (X^a - 1) * ACC[mi], decomposed into two digit polynomials, in forward-transform slot order
-    {
-        const int ar = a & (NTT_N - 1);
-        const bool flip = (a >> 10) & 1;
-#pragma unroll
-        for (int s = 0; s < 32; s++) {
-            const int idx = ntt_in_index(lane, s);
-            i32 c;
-            if (ROTATE) {
-                i32 src = w.acc[(idx - ar) & (NTT_N - 1)];
-                bool neg = (idx < ar) != flip;
-                c = (i32)((neg ? 0u - (u32)src : (u32)src) - (u32)w.acc[idx]);
-            } else {
-                c = w.acc[idx];
-            }
-            i32 d0, d1;
-            decompose(c, d0, d1);
-            v0[s] = ff_from_i32(d0);
-            v1[s] = ff_from_i32(d1);
-        }
-    }
-    NB_LOCKSTEP();
-    // 2. forward transforms of the two digits
-    warp_ntt_forward(v0, w.scratch, w.twd_fwd, lane);
-    warp_ntt_forward(v1, w.scratch, w.twd_fwd, lane);
-    // 3. multiply-accumulate with this warp's half of the key row (tgsw_gpu.py:58-107)
-    {
-        const ulonglong2 *bk = reinterpret_cast<const ulonglong2 *>(bk_row) + (size_t)w.mi * (32 * 2 * 32) + lane;
-#pragma unroll
-        for (int t = 0; t < 32; t++) {
-            ulonglong2 b0 = __ldg(bk + (t * 2 + 0) * 32);
-            ulonglong2 b1 = __ldg(bk + (t * 2 + 1) * 32);
-            u64 p0 = ff_mul2_add(v0[t], b0.x, v1[t], b1.x);      // contribution to output polynomial 0
-            u64 p1 = ff_mul2_add(v0[t], b0.y, v1[t], b1.y);      // contribution to output polynomial 1
-            v0[t] = w.mi ? p1 : p0;
-            w.xchg_out[t * 32 + lane] = w.mi ? p0 : p1;
-            if (t % 4 == 3) NB_LOCKSTEP();
-        }
-    }
-    pair_barrier(w.bar_id);
-#pragma unroll
-    for (int t = 0; t < 32; t++) v0[t] = ff_add(v0[t], w.xchg_in[t * 32 + lane]);
-    pair_barrier(w.bar_id);     // partner finished reading our buffer before the next step rewrites it
-    // 4. inverse transform of output polynomial mi, back to Torus32 (ntt.mako:402-408)
-    warp_ntt_inverse(v0, w.scratch, w.twd_inv, lane);
-#pragma unroll
-    for (int s = 0; s < 32; s++) {
-        const int idx = ntt_in_index(lane, s);
-        i32 r = ff_to_i32(v0[s]);
-        if (ROTATE) w.acc[idx] = (i32)((u32)w.acc[idx] + (u32)r);
-        else w.acc[idx] = r;
-    }
-    __syncwarp();
 }
 
 // mod-switch to [0, 2N) (numeric_functions_gpu.py:55-71)
 NB_HD i32 modswitch_2n(i32 x) { return (i32)(((u32)x + (1u << 20)) >> 21); }
 
-constexpr int BR_CT_PER_CTA = 4;
-constexpr int BR_THREADS = BR_CT_PER_CTA * 64;
-constexpr size_t BR_SMEM_PER_WARP = NTT_N * sizeof(i32) + TR_WORDS * sizeof(u64) + NTT_N * sizeof(u64);
-constexpr size_t BR_SMEM_BYTES = 2 * NTT_N * sizeof(u64) + 2 * BR_CT_PER_CTA * BR_SMEM_PER_WARP;
+// ---- fused bootstrap: CTA-wide phases over shared-memory-resident polynomials (br_phases.cuh) -----
+constexpr size_t BR2_SMEM_ACC = (size_t)BR2_CT * 2 * NTT_N * sizeof(i32);
+constexpr size_t BR2_SMEM_W = (size_t)BR2_POLYS * POLY_STRIDE * sizeof(u64);
+constexpr size_t BR2_SMEM_TWD = 2 * NTT_N * sizeof(u64);
+constexpr size_t BR2_SMEM_BYTES = BR2_SMEM_ACC + BR2_SMEM_W + BR2_SMEM_TWD + 64;
 
 struct BlindRotateArgs {
     // mode A (gate): x = c + s1 * in1 + s2 * in2 is formed on the fly (gates.py prologues), then
@@ -255,111 +166,120 @@ struct BlindRotateArgs {
     const u64 *bk;          // internal layout, n rows
     i32 *out_a, *out_b;     // extracted LWE samples (B,1024), (B,)
     i32 *accum_out;         // optional: final accumulators (B,2,1024)
-    int n;                  // LWE dimension (500)
+    int n;                  // LWE dimension (500); n = 0 with `plain` = one external product
     int extract;            // write out_a/out_b
+    int plain;              // 1: accum <- bk[0] (x) accum, no rotation (tgsw.py:165-172), n ignored
     size_t batch;
 };
 
-__global__ void __launch_bounds__(BR_THREADS, 1) blind_rotate_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g,
-                                                                      const u64 *__restrict__ twd_inv_g)
+struct Br2Smem {
+    i32 *acc;      // [CT][2][1024]
+    u64 *w;        // [16][POLY_STRIDE]
+    u64 *twd_fwd;  // [16][64]
+    u64 *twd_inv;
+    int *rot;      // [2][CT]
+};
+
+NB_D Br2Smem br2_carve(unsigned char *raw)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *twd_fwd = reinterpret_cast<u64 *>(smem_raw);
-    u64 *twd_inv = twd_fwd + NTT_N;
-    for (int i = threadIdx.x; i < NTT_N; i += blockDim.x) { twd_fwd[i] = twd_fwd_g[i]; twd_inv[i] = twd_inv_g[i]; }
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ct_local = warp >> 1, mi = warp & 1;
-    unsigned char *wbase = smem_raw + 2 * NTT_N * sizeof(u64);
-    auto warp_mem = [&](int wi) { return wbase + (size_t)wi * BR_SMEM_PER_WARP; };
-    WarpState w;
-    w.lane = lane; w.mi = mi; w.bar_id = 1 + ct_local;
-    w.acc = reinterpret_cast<i32 *>(warp_mem(warp));
-    w.scratch = reinterpret_cast<u64 *>(warp_mem(warp) + NTT_N * sizeof(i32));
-    w.xchg_out = w.scratch + TR_WORDS;
-    w.xchg_in = reinterpret_cast<u64 *>(warp_mem(warp ^ 1) + NTT_N * sizeof(i32)) + TR_WORDS;
-    w.twd_fwd = twd_fwd; w.twd_inv = twd_inv;
-    __syncthreads();
-
-    const size_t ct = (size_t)blockIdx.x * BR_CT_PER_CTA + ct_local;
-    // Warps of a ciphertext beyond the batch still run (on ciphertext batch-1) so that the named
-    // barriers stay balanced; they just do not store anything.
-    const bool live = ct < p.batch;
-    const size_t c = live ? ct : p.batch - 1;
-    const int n = p.n;
-
-    // accumulator initialisation
-    if (p.accum) {
-        for (int s = 0; s < 32; s++) w.acc[s * 32 + lane] = p.accum[(c * 2 + mi) * NTT_N + s * 32 + lane];
-    } else {
-        // ACC = (0, X^(2N - barb) * [mu, ..., mu])   (bootstrap.py:177-182, 224)
-        i32 xb = p.c + p.s1 * p.in1_b[c] + (p.in2_b ? p.s2 * p.in2_b[c] : 0);
-        int q = 2 * NTT_N - modswitch_2n(xb);
-        for (int s = 0; s < 32; s++) {
-            int x = s * 32 + lane;
-            i32 val;
-            if (q < NTT_N) val = x < q ? (i32)(0u - (u32)p.mu) : p.mu;
-            else val = x < q - NTT_N ? p.mu : (i32)(0u - (u32)p.mu);
-            w.acc[x] = mi ? val : 0;
-        }
-    }
-    __syncwarp();
-
-    for (int i = 0; i < n; i++) {
-        int a;
-        if (p.bara) a = p.bara[c * n + i];
-        else {
-            i32 xa = p.s1 * p.in1_a[c * n + i] + (p.in2_a ? p.s2 * p.in2_a[c * n + i] : 0);
-            a = modswitch_2n(xa);
-        }
-        external_product_step<true>(w, p.bk + (size_t)i * 8 * NTT_N, a);
-    }
-
-    if (live) {
-        if (p.accum_out)
-            for (int s = 0; s < 32; s++) p.accum_out[(ct * 2 + mi) * NTT_N + s * 32 + lane] = w.acc[s * 32 + lane];
-        if (p.extract) {
-            // sample extraction (tlwe_gpu.mako:63-82; blind_rotate.mako:213-224)
-            if (mi == 0) {
-                for (int s = 0; s < 32; s++) {
-                    int x = s * 32 + lane;
-                    p.out_a[ct * NTT_N + x] = x == 0 ? w.acc[0] : (i32)(0u - (u32)w.acc[NTT_N - x]);
-                }
-            } else if (lane == 0) {
-                p.out_b[ct] = w.acc[0];
-            }
-        }
-    }
+    Br2Smem s;
+    s.w = reinterpret_cast<u64 *>(raw);
+    s.twd_fwd = s.w + BR2_POLYS * POLY_STRIDE;
+    s.twd_inv = s.twd_fwd + NTT_N;
+    s.acc = reinterpret_cast<i32 *>(s.twd_inv + NTT_N);
+    s.rot = reinterpret_cast<int *>(s.acc + BR2_CT * 2 * NTT_N);
+    return s;
 }
 
-// stand-alone external product: accum (B,2,1024) <- bk_row (x) accum   (tgsw.py:165-172)
-__global__ void __launch_bounds__(BR_THREADS, 1) external_product_kernel(i32 *accum, const u64 *__restrict__ bk_row,
-                                                                          size_t batch, const u64 *__restrict__ twd_fwd_g,
-                                                                          const u64 *__restrict__ twd_inv_g)
+// rotation amount of ciphertext c at step i
+NB_D int br2_rotation(const BlindRotateArgs &p, size_t c, int i)
+{
+    if (p.bara) return p.bara[c * p.n + i];
+    i32 xa = p.s1 * p.in1_a[c * p.n + i] + (p.in2_a ? p.s2 * p.in2_a[c * p.n + i] : 0);
+    return modswitch_2n(xa);
+}
+
+template <bool ROTATE>
+NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *rot, int tid)
+{
+    // forward transforms of the 16 digit polynomials (4 ciphertexts x 2 polynomials x 2 digits)
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) phase_fwd1<ROTATE>(it * BR2_THREADS + tid, s.acc, s.w, s.twd_fwd, rot);
+    __syncthreads();
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) { int p, r, g; map_fwd2(tid, it, p, r, g); phase_fwd2(p, r, g, s.w); }
+    __syncthreads();
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) { int p, r, u; map_fwd3(tid, it, p, r, u); phase_fwd3(p, r, u, s.w); }
+    __syncthreads();
+    // multiply-accumulate with the key row (tgsw_gpu.py:58-107); each key element is fetched once per CTA
+    phase_mac(tid >> 5, tid & 31, s.w, bk_row);
+    __syncthreads();
+    // inverse transforms of the 8 output polynomials
+    { int p, r, u; map_inv3(tid, p, r, u); phase_inv3(p, r, u, s.w); }
+    __syncthreads();
+    { int p, r, g; map_inv2(tid, p, r, g); phase_inv2(p, r, g, s.w); }
+    __syncthreads();
+    phase_inv1<ROTATE>(tid, s.acc, s.w, s.twd_inv);
+}
+
+__global__ void __launch_bounds__(BR2_THREADS, 1) blind_rotate_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g,
+                                                                       const u64 *__restrict__ twd_inv_g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *twd_fwd = reinterpret_cast<u64 *>(smem_raw);
-    u64 *twd_inv = twd_fwd + NTT_N;
-    for (int i = threadIdx.x; i < NTT_N; i += blockDim.x) { twd_fwd[i] = twd_fwd_g[i]; twd_inv[i] = twd_inv_g[i]; }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ct_local = warp >> 1, mi = warp & 1;
-    unsigned char *wbase = smem_raw + 2 * NTT_N * sizeof(u64);
-    WarpState w;
-    w.lane = lane; w.mi = mi; w.bar_id = 1 + ct_local;
-    w.acc = reinterpret_cast<i32 *>(wbase + (size_t)warp * BR_SMEM_PER_WARP);
-    w.scratch = reinterpret_cast<u64 *>(wbase + (size_t)warp * BR_SMEM_PER_WARP + NTT_N * sizeof(i32));
-    w.xchg_out = w.scratch + TR_WORDS;
-    w.xchg_in = reinterpret_cast<u64 *>(wbase + (size_t)(warp ^ 1) * BR_SMEM_PER_WARP + NTT_N * sizeof(i32)) + TR_WORDS;
-    w.twd_fwd = twd_fwd; w.twd_inv = twd_inv;
-    __syncthreads();
-    const size_t ct = (size_t)blockIdx.x * BR_CT_PER_CTA + ct_local;
-    const bool live = ct < batch;
-    const size_t c = live ? ct : batch - 1;
-    for (int s = 0; s < 32; s++) w.acc[s * 32 + lane] = accum[(c * 2 + mi) * NTT_N + s * 32 + lane];
-    __syncwarp();
-    external_product_step<false>(w, bk_row, 0);
-    if (live)
-        for (int s = 0; s < 32; s++) accum[(ct * 2 + mi) * NTT_N + s * 32 + lane] = w.acc[s * 32 + lane];
+    const Br2Smem s = br2_carve(smem_raw);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NTT_N; i += BR2_THREADS) { s.twd_fwd[i] = twd_fwd_g[i]; s.twd_inv[i] = twd_inv_g[i]; }
+
+    const size_t ct0 = (size_t)blockIdx.x * BR2_CT;
+    // ciphertext slots beyond the batch replay the last ciphertext and store nothing
+    auto ct_of = [&](int slot) { size_t c = ct0 + slot; return c < p.batch ? c : p.batch - 1; };
+
+    // accumulator initialisation: 8 polynomials x 1024 coefficients
+    for (int e = tid; e < BR2_CT * 2 * NTT_N; e += BR2_THREADS) {
+        const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);
+        const size_t c = ct_of(slot);
+        i32 val;
+        if (p.accum) {
+            val = p.accum[(c * 2 + mi) * NTT_N + x];
+        } else {
+            // ACC = (0, X^(2N - barb) * [mu, ..., mu])   (bootstrap.py:177-182, 224)
+            i32 xb = p.c + p.s1 * p.in1_b[c] + (p.in2_b ? p.s2 * p.in2_b[c] : 0);
+            int q = 2 * NTT_N - modswitch_2n(xb);
+            if (q < NTT_N) val = x < q ? (i32)(0u - (u32)p.mu) : p.mu;
+            else val = x < q - NTT_N ? p.mu : (i32)(0u - (u32)p.mu);
+            if (mi == 0) val = 0;
+        }
+        s.acc[e] = val;
+    }
+    if (p.plain) {
+        __syncthreads();
+        br2_step<false>(s, p.bk, s.rot, tid);
+        __syncthreads();
+    } else {
+        if (tid < BR2_CT) s.rot[tid] = br2_rotation(p, ct_of(tid), 0);
+        __syncthreads();
+        for (int i = 0; i < p.n; i++) {
+            int next = 0;
+            if (tid < BR2_CT && i + 1 < p.n) next = br2_rotation(p, ct_of(tid), i + 1);
+            br2_step<true>(s, p.bk + (size_t)i * 8 * NTT_N, s.rot + (i & 1) * BR2_CT, tid);
+            if (tid < BR2_CT) s.rot[((i + 1) & 1) * BR2_CT + tid] = next;
+            __syncthreads();
+        }
+    }
+
+    for (int e = tid; e < BR2_CT * 2 * NTT_N; e += BR2_THREADS) {
+        const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);
+        const size_t c = ct0 + slot;
+        if (c >= p.batch) continue;
+        if (p.accum_out) p.accum_out[(c * 2 + mi) * NTT_N + x] = s.acc[e];
+        if (p.extract) {
+            // sample extraction (tlwe_gpu.mako:63-82; blind_rotate.mako:213-224)
+            const i32 *a0 = s.acc + slot * 2 * NTT_N;
+            if (mi == 0) p.out_a[c * NTT_N + x] = x == 0 ? a0[0] : (i32)(0u - (u32)a0[NTT_N - x]);
+            else if (x == 0) p.out_b[c] = a0[NTT_N];
+        }
+    }
 }
 
 // ---- LWE key switch (lwe_gpu.mako:59-118; lwe_cpu.py:62-93) --------------------------------------

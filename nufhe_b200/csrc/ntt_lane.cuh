@@ -50,7 +50,7 @@ NB_HD int ntt_twiddle_exponent(int lane, int slot)
 }
 
 // One decimation-in-frequency layer set: size 2^LOGN at v[BASE ..], root 2^ROOTLOG.
-template <int LOGN, int ROOTLOG, int BASE> NB_HD void dif_inlane(u64 *v)
+template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dif_inlane(u64 *v)
 {
     constexpr int n = 1 << LOGN;
     static_for<0, LOGN>([&](auto S) {
@@ -59,7 +59,7 @@ template <int LOGN, int ROOTLOG, int BASE> NB_HD void dif_inlane(u64 *v)
         static_for<0, n / 2>([&](auto Q) {
             constexpr int q = decltype(Q)::value;
             constexpr int blk = q / half, k = q % half;
-            constexpr int i0 = BASE + blk * 2 * half + k, i1 = i0 + half;
+            constexpr int i0 = BASE + (blk * 2 * half + k) * STRIDE, i1 = i0 + half * STRIDE;
             u64 a = v[i0], b = v[i1];
             v[i0] = ff_add(a, b);
             v[i1] = ff_shl<(ROOTLOG * k * (1 << s)) % 192>(ff_sub(a, b));
@@ -69,7 +69,7 @@ template <int LOGN, int ROOTLOG, int BASE> NB_HD void dif_inlane(u64 *v)
 }
 
 // The exact inverse network (up to the factor 2^LOGN): decimation in time with the inverse root.
-template <int LOGN, int ROOTLOG, int BASE> NB_HD void dit_inlane(u64 *v)
+template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dit_inlane(u64 *v)
 {
     constexpr int n = 1 << LOGN;
     static_for<0, LOGN>([&](auto S) {
@@ -78,7 +78,7 @@ template <int LOGN, int ROOTLOG, int BASE> NB_HD void dit_inlane(u64 *v)
         static_for<0, n / 2>([&](auto Q) {
             constexpr int q = decltype(Q)::value;
             constexpr int blk = q / half, k = q % half;
-            constexpr int i0 = BASE + blk * 2 * half + k, i1 = i0 + half;
+            constexpr int i0 = BASE + (blk * 2 * half + k) * STRIDE, i1 = i0 + half * STRIDE;
             constexpr int e = (ROOTLOG * k * (1 << s)) % 192;
             u64 a = v[i0], t = ff_shl<(192 - e) % 192>(v[i1]);
             v[i0] = ff_add(a, t);

@@ -6,6 +6,7 @@
 #pragma once
 #include <vector>
 #include "ntt_lane.cuh"
+#include "br_phases.cuh"
 
 namespace nb {
 
@@ -26,6 +27,22 @@ struct NttTables {
                 int e = ntt_twiddle_exponent(lane, slot);
                 fwd[slot * 32 + lane] = h_pow(psi, e);
                 inv[slot * 32 + lane] = h_mul(h_pow(psi_inv, e), n_inv);
+            }
+    }
+};
+
+// Tables of the phase-structured bootstrap kernel (br_phases.cuh): [row][j2], 64 entries per row.
+struct PhaseTables {
+    std::vector<u64> fwd, inv;
+    PhaseTables() : fwd(NTT_N), inv(NTT_N)
+    {
+        const u64 psi = h_pow(ROOT_GEN, (1ULL << 32) / 2048);
+        const u64 psi_inv = h_inv(psi), n_inv = h_inv(NTT_N);
+        for (int row = 0; row < 16; row++)
+            for (int j2 = 0; j2 < 64; j2++) {
+                int e = w_twiddle_exponent(row, j2);
+                fwd[row * 64 + j2] = h_pow(psi, e);
+                inv[row * 64 + j2] = h_mul(h_pow(psi_inv, e), n_inv);
             }
     }
 };
