@@ -48,10 +48,18 @@ def parse_args():
 
 
 def host_cores():
+    """Usable host threads: CPU affinity, capped by a cgroup CPU quota if the container has one."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
 
 
 def measured_peak_hbm():
@@ -193,9 +201,8 @@ def run_b200_arm(args):
             tg = TransformedTGswSampleArray.empty(thr, params.tgsw_params, (LWE_N,))
             ks_lwe = LweSampleArray.empty(thr, params.in_out_params, (N_POLY, 8, 4))
             cloud_key = NuFHECloudKey(params, BootstrapKey(params.in_out_params, tg), LweKeyswitchKey(ks_lwe))
-        ks_lwe = cloud_key.keyswitch_key.lwe
-        for t in (cloud_key.bootstrap_key.tgsw.samples.a.coeffs, ks_lwe.a, ks_lwe.b, ks_lwe.current_variances):
-            dist.broadcast(t, src=0)
+        from nufhe_b200.sharding import cloud_key_tensors, broadcast_tensors
+        broadcast_tensors(cloud_key_tensors(cloud_key), src=0)
         torch.cuda.synchronize()
     vm = ctx.make_virtual_machine(cloud_key)
 
