@@ -62,7 +62,9 @@ int nb_ff_elementwise(nb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b,
                       size_t b_period);
 
 /* ---- bootstrap key: BootstrapKey / TransformedTGswSampleArray (bootstrap.py:44-92, tgsw.py:99-130).
- * Re-lays `rows` reference rows (each 2*2*2*1024 uint64) into the engine's internal row format. */
+ * Re-lays `rows` reference rows (each 2*2*2*1024 uint64) into the engine's internal row format:
+ * nb_bk_row_u64() uint64 per row (the 8 planes re-ordered and un-Montgomery-ed + 2 correction planes). */
+size_t nb_bk_row_u64(void);
 int nb_bk_prepare(nb_ctx *ctx, const uint64_t *bk_ref, uint64_t *bk_int, size_t rows);
 
 /* ---- tgsw_transformed_external_mul (tgsw.py:165-172): accum (B,2,1024) <- bk[row] (x) accum ---- */

@@ -32,6 +32,7 @@ SIGNATURES = {
     'nb_ntt_inverse_i32': [_vp, _vp, _vp, _sz],
     'nb_ntt_inverse_u64': [_vp, _vp, _vp, _sz],
     'nb_ff_elementwise': [_vp, _int, _vp, _vp, _vp, _sz, _sz],
+    'nb_bk_row_u64': [],
     'nb_bk_prepare': [_vp, _vp, _vp, _sz],
     'nb_external_product': [_vp, _vp, _vp, _sz, _sz],
     'nb_blind_rotate': [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz],
@@ -39,7 +40,7 @@ SIGNATURES = {
     'nb_keyswitch': [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _sz, _int, _int, _vp, _vp, _vp, _sz],
     'nb_lwe_affine': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _sz, _sz],
 }
-_RESTYPES = {'nb_ctx_destroy': None, 'nb_last_error': ctypes.c_char_p, 'nb_build_info': ctypes.c_char_p}
+_RESTYPES = {'nb_bk_row_u64': ctypes.c_size_t, 'nb_ctx_destroy': None, 'nb_last_error': ctypes.c_char_p, 'nb_build_info': ctypes.c_char_p}
 
 _lib = None
 

@@ -33,6 +33,12 @@ constexpr int BR2_THREADS = 512;
 constexpr int ROW_STRIDE = 66;                    // u64 per row (64 + 2 padding)
 constexpr int POLY_STRIDE = 16 * ROW_STRIDE;      // u64 per work polynomial
 constexpr int BR2_POLYS = 4 * BR2_CT;             // work polynomials per CTA
+// Engine bootstrap-key row: 8 planes [(mi*2+j)*2+mo][row*64 + stored column] of plain field values plus
+// 2 correction planes K[mo] = 512 * NTT(1,...,1) * sum_{mi,j} plane, because the forward transforms run
+// on the UNSIGNED digits u = d + 512 in [0, 1023] (cheap twist, no sign handling):
+//     sum_d NTT(d) BK = sum_d NTT(u) BK - 512 NTT(1) sum_d BK.
+constexpr int BK_PLANES = 10;
+constexpr int BK_ROW_U64 = BK_PLANES * NTT_N;
 
 // 16-byte accesses to two adjacent field elements (shared memory rows and key rows are 16-byte aligned)
 NB_HD void ld2(const u64 *p, u64 &x, u64 &y)
@@ -77,12 +83,13 @@ NB_HD int w_natural_index(int row, int scol)
 // twiddle exponent (power of psi) applied by fwd1 to (row, j2)
 NB_HD int w_twiddle_exponent(int row, int j2) { return (j2 * (2 * brev(row, 4) + 1)) % 2048; }
 
-// gadget decomposition digit j of one coefficient (tgsw_gpu.py:31-54; blind_rotate.mako:41-43,116-124)
-NB_HD i32 decomp_digit(i32 c, int j)
+// gadget decomposition digit j of one coefficient (tgsw_gpu.py:31-54; blind_rotate.mako:41-43,116-124),
+// returned without the "- 512": u = digit + 512 in [0, 1023]
+NB_HD u32 decomp_udigit(i32 c, int j)
 {
     const u32 offset = 0x80000000u + (1u << 21);
-    i32 t = (i32)((u32)c + offset);
-    return ((t >> (22 - 10 * j)) & 1023) - 512;
+    u32 t = (u32)c + offset;
+    return (t >> (22 - 10 * j)) & 1023u;
 }
 
 // (X^a - 1) * acc at index idx  (polynomials_gpu.mako:18-77 with minus_one; blind_rotate.mako:100-114)
@@ -109,7 +116,7 @@ NB_HD void phase_fwd1(int task, const i32 *acc_all, u64 *w_all, const u64 *twd, 
         constexpr int j1 = decltype(J)::value;
         const int idx = 64 * j1 + j2;
         i32 c = ROTATE ? rotate_minus_one(acc, idx, ar, flip) : acc[idx];
-        v[j1] = ff_shl<6 * j1>(ff_from_i32(decomp_digit(c, j)));
+        v[j1] = ff_twist_small<j1>(decomp_udigit(c, j));
     });
     dif_inlane<4, 12, 0>(v);
     u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
@@ -232,9 +239,9 @@ NB_HD void phase_inv3(int p, int row, int u, u64 *w_all)
 NB_HD void phase_mac(int row, int q, u64 *w_all, const u64 *bk_row)
 {
     const int pos = row * 64 + 2 * q;
-    u64 bk[8][2];
-    static_for<0, 8>([&](auto M) {
-        constexpr int m = decltype(M)::value;            // m = (mi * 2 + j) * 2 + mo
+    u64 bk[BK_PLANES][2];
+    static_for<0, BK_PLANES>([&](auto M) {
+        constexpr int m = decltype(M)::value;            // m = (mi * 2 + j) * 2 + mo; 8 + mo = correction
         ld2_global(bk_row + m * NTT_N + pos, bk[m][0], bk[m][1]);
     });
     for (int ct = 0; ct < BR2_CT; ct++) {
@@ -249,9 +256,9 @@ NB_HD void phase_mac(int row, int q, u64 *w_all, const u64 *bk_row)
             u64 o[2];
             static_for<0, 2>([&](auto X) {
                 constexpr int x = decltype(X)::value;
-                u64 s = ff_mul2_add(f[0][x], bk[0 * 2 + mo][x], f[1][x], bk[1 * 2 + mo][x]);
-                u64 t = ff_mul2_add(f[2][x], bk[2 * 2 + mo][x], f[3][x], bk[3 * 2 + mo][x]);
-                o[x] = ff_add(s, t);
+                const u64 fa[4] = {f[0][x], f[1][x], f[2][x], f[3][x]};
+                const u64 ba[4] = {bk[0 * 2 + mo][x], bk[1 * 2 + mo][x], bk[2 * 2 + mo][x], bk[3 * 2 + mo][x]};
+                o[x] = ff_sub(ff_dot4(fa, ba), bk[8 + mo][x]);
             });
             st2(w + mo * POLY_STRIDE, o[0], o[1]);
         });

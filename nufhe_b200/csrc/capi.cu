@@ -13,6 +13,7 @@ struct nb_ctx {
     cudaStream_t stream;
     u64 *d_twd_fwd, *d_twd_inv;          // warp-NTT tables (stand-alone transforms)
     u64 *d_ph_fwd, *d_ph_inv;            // phase tables (fused bootstrap)
+    u64 *d_ones512;                      // 512 * NTT(all-ones), natural order (bk_prepare)
     int sm_count;
     std::string err;
 };
@@ -46,7 +47,7 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     nb_ctx *ctx = new nb_ctx();
     ctx->device = device;
     ctx->stream = (cudaStream_t)stream;
-    ctx->d_twd_fwd = ctx->d_twd_inv = ctx->d_ph_fwd = ctx->d_ph_inv = nullptr;
+    ctx->d_twd_fwd = ctx->d_twd_inv = ctx->d_ph_fwd = ctx->d_ph_inv = ctx->d_ones512 = nullptr;
     *out = ctx;   // returned even on failure so that nb_last_error() can be read; caller destroys it
     NB_TRY(check(ctx, cudaSetDevice(device), "cudaSetDevice"));
     cudaDeviceProp prop;
@@ -65,6 +66,8 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     NB_TRY(check(ctx, cudaMalloc(&ctx->d_ph_inv, NTT_N * sizeof(u64)), "cudaMalloc"));
     NB_TRY(check(ctx, cudaMemcpy(ctx->d_ph_fwd, pt.fwd.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
     NB_TRY(check(ctx, cudaMemcpy(ctx->d_ph_inv, pt.inv.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
+    NB_TRY(check(ctx, cudaMalloc(&ctx->d_ones512, NTT_N * sizeof(u64)), "cudaMalloc"));
+    NB_TRY(check(ctx, cudaMemcpy(ctx->d_ones512, pt.ones512.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)BR2_SMEM_BYTES), "cudaFuncSetAttribute(blind_rotate)"));
     return NB_OK;
@@ -78,6 +81,7 @@ void nb_ctx_destroy(nb_ctx *ctx)
     if (ctx->d_twd_inv) cudaFree(ctx->d_twd_inv);
     if (ctx->d_ph_fwd) cudaFree(ctx->d_ph_fwd);
     if (ctx->d_ph_inv) cudaFree(ctx->d_ph_inv);
+    if (ctx->d_ones512) cudaFree(ctx->d_ones512);
     delete ctx;
 }
 
@@ -176,13 +180,16 @@ int nb_ff_elementwise(nb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b,
     return launch_check(ctx, "ff_elementwise_kernel");
 }
 
+size_t nb_bk_row_u64(void) { return BK_ROW_U64; }
+
 int nb_bk_prepare(nb_ctx *ctx, const uint64_t *bk_ref, uint64_t *bk_int, size_t rows)
 {
     if (!ctx || !bk_ref || !bk_int) return fail(ctx, NB_EINVAL, "nb_bk_prepare: null argument");
     if (rows == 0) return NB_OK;
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
-    size_t total = rows * 8 * NTT_N, blocks = (total + 255) / 256, cap = (size_t)ctx->sm_count * 16;
-    bk_prepare_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>((const u64 *)bk_ref, (u64 *)bk_int, rows);
+    size_t total = rows * NTT_N, blocks = (total + 255) / 256, cap = (size_t)ctx->sm_count * 16;
+    bk_prepare_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>((const u64 *)bk_ref, (u64 *)bk_int,
+                                                                                  ctx->d_ones512, rows);
     return launch_check(ctx, "bk_prepare_kernel");
 }
 
@@ -192,7 +199,7 @@ int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, siz
     if (batch == 0) return NB_OK;
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
     BlindRotateArgs p{};
-    p.accum = accum; p.accum_out = accum; p.bk = (const u64 *)bk_int + bk_row * 8 * NTT_N;
+    p.accum = accum; p.accum_out = accum; p.bk = (const u64 *)bk_int + bk_row * BK_ROW_U64;
     p.plain = 1; p.batch = batch;
     int grid = (int)((batch + BR2_CT - 1) / BR2_CT);
     blind_rotate_kernel<<<grid, BR2_THREADS, BR2_SMEM_BYTES, ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);

@@ -39,6 +39,18 @@ typedef int32_t i32;
 constexpr u64 FF_P = 0xffffffff00000001ULL;
 constexpr u64 FF_EPS = 0xffffffffULL;   // 2^64 mod p
 
+#if defined(__CUDACC__)
+// Multipliers read from the constant bank so that ptxas keeps them as IMAD.WIDE operands (FMA pipe)
+// instead of strength-reducing to SHF/IADD3 on the ALU pipe, which is the binding pipe of every kernel
+// here (profiles/r1_v2_analysis.md).
+__constant__ u32 nb_c_pow2[32] = {
+    1u << 0, 1u << 1, 1u << 2, 1u << 3, 1u << 4, 1u << 5, 1u << 6, 1u << 7, 1u << 8, 1u << 9, 1u << 10,
+    1u << 11, 1u << 12, 1u << 13, 1u << 14, 1u << 15, 1u << 16, 1u << 17, 1u << 18, 1u << 19, 1u << 20,
+    1u << 21, 1u << 22, 1u << 23, 1u << 24, 1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30,
+    1u << 31};
+__constant__ u32 nb_c_eps = 0xffffffffu;
+#endif
+
 NB_HD u32 lo32(u64 x) { return (u32)x; }
 NB_HD u32 hi32(u64 x) { return (u32)(x >> 32); }
 NB_HD u64 pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
@@ -73,7 +85,14 @@ NB_HD u64 ff_neg(u64 a) { return a ? FF_P - a : 0; }
 NB_HD u64 ff_add(u64 a, u64 b) { return ff_sub(a, FF_P - b); }
 
 // v * (2^32 - 1) for a 32-bit v: always canonical ((2^32-1)^2 < p).
-NB_HD u64 ff_eps_mul(u32 v) { return ((u64)v << 32) - v; }
+NB_HD u64 ff_eps_mul(u32 v)
+{
+#if defined(__CUDA_ARCH__)
+    return (u64)v * (u64)nb_c_eps;
+#else
+    return ((u64)v << 32) - v;
+#endif
+}
 
 // 128-bit (hi:lo) -> canonical  (arithmetic.mako:197-333 `mul`, reduction part :200-207)
 NB_HD u64 ff_reduce128(u64 lo, u64 hi)
@@ -102,6 +121,50 @@ NB_HD u64 ff_mul2_add(u64 a, u64 b, u64 c, u64 d)
     return ff_add(ff_mul(a, b), ff_mul(c, d));
 }
 
+// a0*b0 + a1*b1 + a2*b2 + a3*b3 mod p: the four 128-bit products are summed first (130 bits) and
+// folded once; 2^128 = phi^4 = -phi.
+NB_HD u64 ff_dot4(const u64 *a, const u64 *b)
+{
+#if defined(__CUDA_ARCH__)
+    u64 lo = a[0] * b[0], hi = __umul64hi(a[0], b[0]);
+    u32 c = 0;
+#pragma unroll
+    for (int k = 1; k < 4; k++) {
+        u64 pl = a[k] * b[k], ph = __umul64hi(a[k], b[k]);
+        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+            : "+l"(lo), "+l"(hi), "+r"(c) : "l"(pl), "l"(ph));
+    }
+#else
+    unsigned __int128 acc = 0;
+    u32 c = 0;
+    for (int k = 0; k < 4; k++) {
+        unsigned __int128 pr = (unsigned __int128)a[k] * b[k];
+        unsigned __int128 nx = acc + pr;
+        c += nx < acc;
+        acc = nx;
+    }
+    u64 lo = (u64)acc, hi = (u64)(acc >> 64);
+#endif
+    return ff_sub(ff_reduce128(lo, hi), (u64)c << 32);
+}
+
+// u * 2^(6*J1) for a small unsigned u < 2^10 (gadget digit + 512): the twist of the inner 16-point
+// transform without a general shift.  Result canonical.
+template <int J1> NB_HD u64 ff_twist_small(u32 u)
+{
+    constexpr int s = 6 * J1;
+    if constexpr (s <= 54) {
+        return (u64)u << s;                                        // <= 1023 * 2^54 < p
+    } else if constexpr (s == 60) {
+        return ((u64)(u & 15) << 60) + ff_eps_mul(u >> 4);         // (u>>4)*2^64 + (u&15)*2^60, no wrap
+    } else if constexpr (s < 90) {
+        return ff_eps_mul(u << (s - 64));                          // u*2^(s-64) < 2^32, times 2^64
+    } else {
+        // s == 90: u*2^26 = w0 + w1*2^32; times 2^64: w0*eps + w1*2^96 = w0*eps - w1
+        return ff_sub(ff_eps_mul((u & 63) << 26), (u64)(u >> 6));
+    }
+}
+
 // a * b * 2^-64 mod p, the reference's Montgomery product (arithmetic.mako:355-419 `mul_prepared`)
 constexpr u64 FF_RINV = 0xfffffffe00000001ULL;     // 2^-64 mod p (polynomial_transform_ntt.py:66)
 NB_HD u64 ff_mul_prepared(u64 a, u64 b) { return ff_mul(ff_mul(a, b), FF_RINV); }
@@ -123,6 +186,15 @@ NB_HD Limbs3 ff_bitshift(u64 x, int r)     // r in [0, 32)
 {
     Limbs3 y;
     u32 x0 = lo32(x), x1 = hi32(x);
+#if defined(__CUDA_ARCH__)
+    {
+        const u32 k = nb_c_pow2[r];
+        u64 t = (u64)x0 * (u64)k;
+        u64 u = (u64)x1 * (u64)k + (u64)hi32(t);
+        y.y0 = lo32(t); y.y1 = lo32(u); y.y2 = hi32(u);
+        return y;
+    }
+#endif
     if (r == 0) { y.y0 = x0; y.y1 = x1; y.y2 = 0; }
     else {
         y.y0 = x0 << r;

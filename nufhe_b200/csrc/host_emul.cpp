@@ -63,15 +63,21 @@ void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct
     static PhaseTables T;
     std::vector<i32> acc(BR2_CT * 2 * NTT_N, 0);
     std::vector<u64> w(BR2_POLYS * POLY_STRIDE, 0);
-    std::vector<u64> bk(8 * NTT_N);
+    std::vector<u64> bk(BK_ROW_U64);
     for (int c = 0; c < nct; c++) memcpy(&acc[c * 2 * NTT_N], acc_io + c * 2 * NTT_N, sizeof(i32) * 2 * NTT_N);
     int rots[BR2_CT] = {0, 0, 0, 0};
     if (rot) for (int c = 0; c < nct; c++) rots[c] = rot[c];
     // bk_prepare: internal [m][row*64 + scol] plain
-    for (int m = 0; m < 8; m++)
-        for (int row = 0; row < 16; row++)
-            for (int sc = 0; sc < 64; sc++)
-                bk[m * NTT_N + row * 64 + sc] = ff_mul(ff_canon(bk_ref_row[m * NTT_N + w_natural_index(row, sc)]), FF_RINV);
+    for (int pos = 0; pos < NTT_N; pos++) {
+        const int k = w_natural_index(pos >> 6, pos & 63);
+        u64 sum[2] = {0, 0};
+        for (int m = 0; m < 8; m++) {
+            u64 x = ff_mul(ff_canon(bk_ref_row[m * NTT_N + k]), FF_RINV);
+            bk[m * NTT_N + pos] = x;
+            sum[m & 1] = ff_add(sum[m & 1], x);
+        }
+        for (int mo = 0; mo < 2; mo++) bk[(8 + mo) * NTT_N + pos] = ff_mul(sum[mo], T.ones512[k]);
+    }
     for (int it = 0; it < 2; it++)
         for (int tid = 0; tid < BR2_THREADS; tid++) {
             if (rot) phase_fwd1<true>(it * BR2_THREADS + tid, acc.data(), w.data(), T.fwd.data(), rots);

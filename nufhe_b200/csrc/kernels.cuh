@@ -134,16 +134,24 @@ __global__ void ff_elementwise_kernel(int op, const u64 *__restrict__ a, const u
 // reference row (nufhe/blind_rotate.py:112): [mi][j][mo][k], values NTT(bk) * 2^64 (Montgomery form).
 // internal row: [m = (mi*2+j)*2+mo][row * 64 + stored column] (br_phases.cuh), plain values, so that the
 // MAC phase reads, per thread, one 16-byte pair from each of the 8 planes, coalesced across the CTA.
-__global__ void bk_prepare_kernel(const u64 *__restrict__ bk_ref, u64 *__restrict__ bk_int, size_t rows)
+// One thread per (row, position): 8 plain planes + the 2 correction planes (br_phases.cuh: BK_PLANES).
+__global__ void bk_prepare_kernel(const u64 *__restrict__ bk_ref, u64 *__restrict__ bk_int,
+                                  const u64 *__restrict__ ones512, size_t rows)
 {
-    const size_t total = rows * 8 * NTT_N;
+    const size_t total = rows * NTT_N;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        size_t row = i / (8 * NTT_N);
-        int r = (int)(i % (8 * NTT_N));
-        int m = r >> 10, pos = r & 1023;
-        int k = w_natural_index(pos >> 6, pos & 63);
-        u64 x = bk_ref[row * 8 * NTT_N + m * NTT_N + k];
-        bk_int[i] = ff_mul(ff_canon(x), FF_RINV);
+        const size_t row = i >> 10;
+        const int pos = (int)(i & 1023);
+        const int k = w_natural_index(pos >> 6, pos & 63);
+        u64 sum[2] = {0, 0};
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            u64 x = ff_mul(ff_canon(bk_ref[row * 8 * NTT_N + m * NTT_N + k]), FF_RINV);
+            bk_int[row * BK_ROW_U64 + m * NTT_N + pos] = x;
+            sum[m & 1] = ff_add(sum[m & 1], x);
+        }
+        bk_int[row * BK_ROW_U64 + 8 * NTT_N + pos] = ff_mul(sum[0], ones512[k]);
+        bk_int[row * BK_ROW_U64 + 9 * NTT_N + pos] = ff_mul(sum[1], ones512[k]);
     }
 }
 
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(BR2_THREADS, 1) blind_rotate_kernel(BlindRotat
         for (int i = 0; i < p.n; i++) {
             int next = 0;
             if (tid < BR2_CT && i + 1 < p.n) next = br2_rotation(p, ct_of(tid), i + 1);
-            br2_step<true>(s, p.bk + (size_t)i * 8 * NTT_N, s.rot + (i & 1) * BR2_CT, tid);
+            br2_step<true>(s, p.bk + (size_t)i * BK_ROW_U64, s.rot + (i & 1) * BR2_CT, tid);
             if (tid < BR2_CT) s.rot[((i + 1) & 1) * BR2_CT + tid] = next;
             __syncthreads();
         }

@@ -34,8 +34,17 @@ struct NttTables {
 // Tables of the phase-structured bootstrap kernel (br_phases.cuh): [row][j2], 64 entries per row.
 struct PhaseTables {
     std::vector<u64> fwd, inv;
-    PhaseTables() : fwd(NTT_N), inv(NTT_N)
+    std::vector<u64> ones512;   // 512 * NTT(1,1,...,1)[k] in natural order: 512 * 2 / (1 - psi^(2k+1))
+    PhaseTables() : fwd(NTT_N), inv(NTT_N), ones512(NTT_N)
     {
+        {
+            const u64 psi0 = h_pow(ROOT_GEN, (1ULL << 32) / 2048);
+            for (int k = 0; k < NTT_N; k++) {
+                u64 r = h_pow(psi0, 2 * k + 1);
+                u64 denom = (FF_P + 1 - r) % FF_P;          // 1 - r
+                ones512[k] = h_mul(1024, h_inv(denom));     // sum_j r^j = (1 - r^1024) / (1 - r) = 2 / (1 - r)
+            }
+        }
         const u64 psi = h_pow(ROOT_GEN, (1ULL << 32) / 2048);
         const u64 psi_inv = h_inv(psi), n_inv = h_inv(NTT_N);
         for (int row = 0; row < 16; row++)

@@ -115,7 +115,7 @@ class Engine:
     def bk_prepare(self, bk_ref):
         bk_ref = self._dense(bk_ref, torch.int64)
         rows = bk_ref.numel() // (8 * N)
-        out = self.empty((rows, 8, N), torch.int64)
+        out = self.empty((rows, self.lib.nb_bk_row_u64()), torch.int64)
         self._call('nb_bk_prepare', _ptr(bk_ref), _ptr(out), rows)
         return out
 

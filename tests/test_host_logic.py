@@ -160,3 +160,19 @@ def test_lane_field_ops_match_oracle(emul, golden):
     si = s.astype(numpy.int32)
     emul.emul_ff_shl_var(_p(a), _p(si), _p(out), n)
     assert (out == g['lsh']).all()
+
+
+def test_phase_structured_step_matches_oracle(emul):
+    """csrc/br_phases.cuh (the fused bootstrap's CTA-wide phases) executed on the host: plain external
+    product and one rotate-and-accumulate CMux step, random field key, edge rotation amounts."""
+    rng = G.rs(77)
+    bk = G.ff_numbers(rng, (2, 2, 2, 2, 1024))
+    for nct in (1, 3, 4):
+        acc = G.torus32(rng, (nct, 2, 1024))
+        a = acc.copy()
+        emul.emul_phase_step(_p(a), _p(bk[1]), None, ctypes.c_int(nct))
+        assert (a == O.tgsw_external_mul(acc, bk, 1)).all()
+        rot = numpy.array([0, 1024, 1023, 2047][:nct], numpy.int32)
+        a = acc.copy()
+        emul.emul_phase_step(_p(a), _p(bk[0]), _p(rot), ctypes.c_int(nct))
+        assert (a == O.blind_rotate(acc, bk[0:1], rot.reshape(nct, 1))).all()
