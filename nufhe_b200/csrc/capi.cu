@@ -249,20 +249,27 @@ int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, cons
     if (!ctx || !src1_a || !src1_b || !ks_a || !ks_b || !ks_cv || !res_a || !res_b)
         return fail(ctx, NB_EINVAL, "nb_keyswitch: null argument");
     if ((src2_a == nullptr) != (src2_b == nullptr)) return fail(ctx, NB_EINVAL, "nb_keyswitch: src2_a/src2_b must come together");
-    if (n + 1 > KS_THREADS) return fail(ctx, NB_EUNSUPPORTED, "nb_keyswitch: output LWE dimension above 511");
+    if (n + 1 > 512) return fail(ctx, NB_EUNSUPPORTED, "nb_keyswitch: output LWE dimension above 511");
     if (t < 1 || log2_base < 1 || t * log2_base > 31) return fail(ctx, NB_EINVAL, "nb_keyswitch: bad decomposition");
-    size_t smem = (size_t)KS_TILE * in_size * sizeof(i32);
-    if (smem > 200 * 1024) return fail(ctx, NB_EUNSUPPORTED, "nb_keyswitch: input LWE dimension too large");
     if (batch == 0) return NB_OK;
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
-    NB_TRY(check(ctx, cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "cudaFuncSetAttribute(keyswitch)"));
     KeyswitchArgs p{};
     p.src1_a = src1_a; p.src1_b = src1_b; p.src2_a = src2_a; p.src2_b = src2_b; p.c = c;
     p.ks_a = ks_a; p.ks_b = ks_b; p.ks_cv = ks_cv; p.res_a = res_a; p.res_b = res_b; p.res_cv = res_cv;
     p.in_size = (int)in_size; p.n = (int)n; p.t = t; p.log2_base = log2_base; p.batch = batch;
-    int grid = (int)((batch + KS_TILE - 1) / KS_TILE);
-    keyswitch_kernel<<<grid, KS_THREADS, smem, ctx->stream>>>(p);
+    if (t == 8 && log2_base == 2 && in_size == (size_t)KS_IN && n == (size_t)KS_N) {
+        NB_TRY(check(ctx, cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)KS_SMEM_BYTES), "cudaFuncSetAttribute(keyswitch)"));
+        // one wave if possible: spread the batch over the SMs, at most KS_TILE ciphertexts per CTA
+        size_t tile = (batch + ctx->sm_count - 1) / ctx->sm_count;
+        if (tile > KS_TILE) tile = KS_TILE;
+        if (tile < 1) tile = 1;
+        p.tile = (int)tile;
+        int grid = (int)((batch + tile - 1) / tile);
+        keyswitch_kernel<<<grid, KS_THREADS, KS_SMEM_BYTES, ctx->stream>>>(p);
+    } else {
+        keyswitch_generic_kernel<<<(int)batch, 512, 0, ctx->stream>>>(p);
+    }
     return launch_check(ctx, "keyswitch_kernel");
 }
 

@@ -291,11 +291,26 @@ __global__ void __launch_bounds__(BR2_THREADS, 1) blind_rotate_kernel(BlindRotat
 }
 
 // ---- LWE key switch (lwe_gpu.mako:59-118; lwe_cpu.py:62-93) --------------------------------------
-// One CTA handles KS_TILE ciphertexts; thread i owns output coefficient i (i = n: the b term) of all
-// of them, so each key row is fetched once per tile.  src = src1 (+ src2) (+ (0, c)) lets gate_mux
-// fold `(0,1/8) + u1 + u2` (gates.py:657-664) into the load.
-constexpr int KS_TILE = 8;
-constexpr int KS_THREADS = 512;
+// res_a[i] = - sum_{j,k} ks_a[j][k][digit(j,k)][i], res_b = b - sum ks_b[j][k][digit].
+//
+// The reference gathers one 2000-byte key row per (ciphertext, j, k) from global memory: ~12 MB of key
+// per ciphertext.  Here a CTA owns a tile of up to KS_TILE ciphertexts and streams the key ONCE per tile:
+// a producer warp moves the three non-zero rows of each (j, k) into a ring of shared-memory stages with
+// cp.async.bulk (TMA, completion on an mbarrier); 8 consumer warps (thread t owns output coefficients
+// 2t, 2t+1 of every ciphertext of the tile) pick the row with the warp-uniform 2-bit digit and subtract.
+// Stage rows are 2048 bytes apart and row 0 of every stage is a permanent zero row (the key's d = 0 row
+// is zero padding, lwe_cpu.py:31-33), so "digit -> byte offset" is one shift and the address is one LOP3:
+// 2.5 instructions per (ciphertext, j, k, coefficient).
+// src = src1 (+ src2) (+ (0, c)) lets gate_mux fold `(0,1/8) + u1 + u2` (gates.py:657-664) into the load.
+constexpr int KS_TILE = 32;                 // ciphertexts per CTA (run-time tile <= KS_TILE)
+constexpr int KS_CONSUMERS = 256;           // threads 0..249: a[2t], a[2t+1]; thread 250: b and variance
+constexpr int KS_THREADS = KS_CONSUMERS + 32;
+constexpr int KS_STAGES = 8;                // == t, so that stage == k at compile time
+constexpr int KS_ROW_BYTES = 2048;
+constexpr int KS_STAGE_BYTES = 4 * KS_ROW_BYTES;
+constexpr int KS_IN = 1024, KS_N = 500;     // fast-path sizes (api_low_level.py:49-50)
+// + KS_STAGE_BYTES of slack: the stage ring is aligned to 8192 bytes so that the row offset can be OR-ed in
+constexpr size_t KS_SMEM_BYTES = (size_t)(KS_STAGES + 1) * KS_STAGE_BYTES + (size_t)KS_IN * KS_TILE * 2 + 2 * KS_STAGES * 8 + 16;
 
 struct KeyswitchArgs {
     const i32 *src1_a, *src1_b, *src2_a, *src2_b;   // (B, in), (B,)
@@ -305,59 +320,186 @@ struct KeyswitchArgs {
     i32 *res_a, *res_b;                              // (B, n), (B,)
     float *res_cv;                                   // optional
     int in_size, n, t, log2_base;
+    int tile;                                        // ciphertexts per CTA (fast path)
     size_t batch;
 };
 
-__global__ void __launch_bounds__(KS_THREADS) keyswitch_kernel(KeyswitchArgs p)
+NB_D u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+NB_D void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+NB_D void mbar_expect_tx(u64 *bar, u32 bytes)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    i32 *tile_a = reinterpret_cast<i32 *>(smem_raw);            // KS_TILE * in_size, with the rounding offset added
-    const size_t ct0 = (size_t)blockIdx.x * KS_TILE;
-    const int nct = (int)min((size_t)KS_TILE, p.batch - ct0);
-    const int base = 1 << p.log2_base;
-    const u32 prec_offset = 1u << (32 - (1 + p.log2_base * p.t));
-    for (int idx = threadIdx.x; idx < KS_TILE * p.in_size; idx += blockDim.x) {
-        int q = idx / p.in_size, j = idx % p.in_size;
-        i32 v = 0;
-        if (q < nct) {
-            v = p.src1_a[(ct0 + q) * p.in_size + j];
-            if (p.src2_a) v = (i32)((u32)v + (u32)p.src2_a[(ct0 + q) * p.in_size + j]);
-        }
-        tile_a[idx] = (i32)((u32)v + prec_offset);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+NB_D void mbar_arrive(u64 *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+NB_D void mbar_wait(u64 *bar, u32 parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+NB_D void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Fast path: in = 1024, n = 500, t = 8, base = 4 (the scheme's parameters, api_low_level.py:49-56).
+__global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *stages = smem_raw + ((KS_STAGE_BYTES - (smem_u32(smem_raw) & (KS_STAGE_BYTES - 1))) & (KS_STAGE_BYTES - 1));
+    unsigned short *digits = reinterpret_cast<unsigned short *>(stages + KS_STAGES * KS_STAGE_BYTES);  // [j][KS_TILE]
+    u64 *full = reinterpret_cast<u64 *>(stages + KS_STAGES * KS_STAGE_BYTES + KS_IN * KS_TILE * 2);
+    u64 *empty = full + KS_STAGES;
+
+    const int tid = threadIdx.x;
+    const size_t ct0 = (size_t)blockIdx.x * p.tile;
+    const int nct = (int)min((size_t)p.tile, p.batch - ct0);
+
+    if (tid == 0) {
+        for (int s = 0; s < KS_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], KS_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // zero rows (row 0 of every stage) and the packed digits of the tile
+    for (int e = tid; e < KS_STAGES * (KS_ROW_BYTES / 4); e += KS_THREADS)
+        reinterpret_cast<u32 *>(stages + (e / (KS_ROW_BYTES / 4)) * KS_STAGE_BYTES)[e % (KS_ROW_BYTES / 4)] = 0;
+    const u32 prec_offset = 1u << (32 - (1 + 2 * 8));
+    for (int idx = tid; idx < KS_TILE * KS_IN; idx += KS_THREADS) {
+        const int q = idx / KS_IN, j = idx % KS_IN;
+        u32 v = 0;
+        if (q < nct) {
+            v = (u32)p.src1_a[(ct0 + q) * KS_IN + j];
+            if (p.src2_a) v += (u32)p.src2_a[(ct0 + q) * KS_IN + j];
+            v = (v + prec_offset) >> 16;              // the 8 two-bit digits, k = 0 in the top bits
+        }
+        digits[j * KS_TILE + q] = (unsigned short)v;  // ciphertexts beyond nct: all digits 0 -> zero row
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    const int i = threadIdx.x;
-    const bool is_a = i < p.n, is_b = i == p.n;
-    u32 acc[KS_TILE];
-    float cv[KS_TILE];
+
+    if (tid >= KS_CONSUMERS) {
+        // ---- producer warp: one lane streams rows d = 1..3 of (j, k) into stage k ----------------
+        if (tid == KS_CONSUMERS) {
+            for (int j = 0; j < KS_IN; j++) {
+                const u32 parity = (j & 1) ^ 1;
+#pragma unroll 1
+                for (int k = 0; k < KS_STAGES; k++) {
+                    mbar_wait(&empty[k], parity);     // first pass: passes immediately (phase -1 "complete")
+                    mbar_expect_tx(&full[k], 3 * KS_N * 4);
+                    const i32 *src = p.ks_a + ((size_t)(j * 8 + k) * 4 + 1) * KS_N;
+                    unsigned char *dst = stages + k * KS_STAGE_BYTES;
 #pragma unroll
-    for (int q = 0; q < KS_TILE; q++) { acc[q] = 0; cv[q] = 0.f; }
-    if (is_a || is_b) {
-        for (int j = 0; j < p.in_size; j++) {
-            for (int k = 0; k < p.t; k++) {
-                const size_t row0 = ((size_t)j * p.t + k) * base;
-                const int shift = 32 - (k + 1) * p.log2_base;
+                    for (int d = 1; d < 4; d++)
+                        bulk_g2s(dst + d * KS_ROW_BYTES, src + (d - 1) * KS_N, KS_N * 4, &full[k]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers -------------------------------------------------------------------------------
+    const bool is_a = tid < KS_N / 2, is_b = tid == KS_N / 2;
+    const int lane = tid & 31;
+    u32 acc0[KS_TILE], acc1[KS_TILE];
+#pragma unroll
+    for (int q = 0; q < KS_TILE; q++) { acc0[q] = 0; acc1[q] = 0; }
+    // thread 250 (the b column) keeps the float32 variance sums in acc1 (bit patterns)
+    // byte offset of this thread's pair inside a stage row; idle threads read the zero row harmlessly
+    const u32 col_off = is_a ? (u32)tid * 8u : 0u;
+    const u32 stage_base = smem_u32(stages);
+
+    for (int j = 0; j < KS_IN; j++) {
+        // packed digits of the tile for this j: KS_TILE x u16 = 64 bytes
+        u32 w[KS_TILE / 2];
+        {
+            const uint4 *dg = reinterpret_cast<const uint4 *>(digits + j * KS_TILE);
+#pragma unroll
+            for (int x = 0; x < KS_TILE / 8; x++) {
+                uint4 t = dg[x];
+                w[4 * x] = t.x; w[4 * x + 1] = t.y; w[4 * x + 2] = t.z; w[4 * x + 3] = t.w;
+            }
+        }
+        const u32 parity = j & 1;
+#pragma unroll
+        for (int k = 0; k < KS_STAGES; k++) {
+            mbar_wait(&full[k], parity);
+            const u32 base = stage_base + k * KS_STAGE_BYTES + col_off;
+            if (is_b) {
+                const int4 kb = __ldg(reinterpret_cast<const int4 *>(p.ks_b + (size_t)(j * 8 + k) * 4));
+                const float4 kc = __ldg(reinterpret_cast<const float4 *>(p.ks_cv + (size_t)(j * 8 + k) * 4));
 #pragma unroll
                 for (int q = 0; q < KS_TILE; q++) {
-                    int d = (tile_a[q * p.in_size + j] >> shift) & (base - 1);
-                    if (d != 0) {          // the d = 0 row is the zero padding (lwe_cpu.py:31-33)
-                        if (is_a) acc[q] -= (u32)__ldg(p.ks_a + (row0 + d) * p.n + i);
-                        else { acc[q] -= (u32)__ldg(p.ks_b + row0 + d); cv[q] += __ldg(p.ks_cv + row0 + d); }
-                    }
+                    const u32 d = (w[q >> 1] >> (16 * (q & 1) + 14 - 2 * k)) & 3u;
+                    acc0[q] -= d == 1 ? (u32)kb.y : d == 2 ? (u32)kb.z : d == 3 ? (u32)kb.w : 0u;
+                    const float c = d == 1 ? kc.y : d == 2 ? kc.z : d == 3 ? kc.w : 0.f;
+                    acc1[q] = __float_as_uint(__uint_as_float(acc1[q]) + c);
                 }
-            }
-        }
+            } else {
 #pragma unroll
-        for (int q = 0; q < KS_TILE; q++) {
-            if (q < nct) {
-                if (is_a) p.res_a[(ct0 + q) * p.n + i] = (i32)acc[q];
-                else {
-                    u32 b = (u32)p.src1_b[ct0 + q] + (p.src2_b ? (u32)p.src2_b[ct0 + q] : 0u) + (u32)p.c;
-                    p.res_b[ct0 + q] = (i32)(b + acc[q]);
-                    if (p.res_cv) p.res_cv[ct0 + q] = cv[q];
+                for (int q = 0; q < KS_TILE; q++) {
+                    // digit (2 bits) moved to bits 11..12 = row * 2048
+                    const int pos = 16 * (q & 1) + 14 - 2 * k;          // bit position of the digit
+                    const u32 sh = pos >= 11 ? (w[q >> 1] >> (pos - 11)) : (w[q >> 1] << (11 - pos));
+                    const u32 addr = (sh & 0x1800u) | base;            // base has bits 11..12 clear
+                    u32 v0, v1;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(addr));
+                    acc0[q] -= v0;
+                    acc1[q] -= v1;
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[k]);
         }
+    }
+
+#pragma unroll
+    for (int q = 0; q < KS_TILE; q++) {
+        if (q < nct) {
+            if (is_a) {
+                p.res_a[(ct0 + q) * KS_N + 2 * tid] = (i32)acc0[q];
+                p.res_a[(ct0 + q) * KS_N + 2 * tid + 1] = (i32)acc1[q];
+            } else if (is_b) {
+                u32 b = (u32)p.src1_b[ct0 + q] + (p.src2_b ? (u32)p.src2_b[ct0 + q] : 0u) + (u32)p.c;
+                p.res_b[ct0 + q] = (i32)(b + acc0[q]);
+                if (p.res_cv) p.res_cv[ct0 + q] = __uint_as_float(acc1[q]);
+            }
+        }
+    }
+}
+
+// Generic decomposition parameters (API parity with LweKeyswitch(…, decomp_length, log2_base)): the
+// straightforward per-ciphertext gather.
+__global__ void __launch_bounds__(512) keyswitch_generic_kernel(KeyswitchArgs p)
+{
+    const size_t ct = blockIdx.x;
+    const int base = 1 << p.log2_base;
+    const u32 prec_offset = 1u << (32 - (1 + p.log2_base * p.t));
+    const int i = threadIdx.x;
+    const bool is_a = i < p.n, is_b = i == p.n;
+    if (!(is_a || is_b)) return;
+    u32 acc = 0;
+    float cv = 0.f;
+    for (int j = 0; j < p.in_size; j++) {
+        u32 v = (u32)p.src1_a[ct * p.in_size + j];
+        if (p.src2_a) v += (u32)p.src2_a[ct * p.in_size + j];
+        const i32 tmp = (i32)(v + prec_offset);
+        for (int k = 0; k < p.t; k++) {
+            const int d = (tmp >> (32 - (k + 1) * p.log2_base)) & (base - 1);
+            if (d == 0) continue;                    // zero padding row (lwe_gpu.mako:97-106)
+            const size_t row = ((size_t)j * p.t + k) * base + d;
+            if (is_a) acc -= (u32)__ldg(p.ks_a + row * p.n + i);
+            else { acc -= (u32)__ldg(p.ks_b + row); cv += __ldg(p.ks_cv + row); }
+        }
+    }
+    if (is_a) p.res_a[ct * p.n + i] = (i32)acc;
+    else {
+        u32 b = (u32)p.src1_b[ct] + (p.src2_b ? (u32)p.src2_b[ct] : 0u) + (u32)p.c;
+        p.res_b[ct] = (i32)(b + acc);
+        if (p.res_cv) p.res_cv[ct] = cv;
     }
 }
 
