@@ -86,6 +86,7 @@ def cpu_gate_sample(sample, gate):
     """Time the CPU oracle port on `sample` gates with all host threads.  Returns gates/s."""
     import numpy
     from oracle import oracle as O
+    O.set_threads(host_cores())
     keys = cpu_gate_sample.keys
     if keys is None:
         keys = cpu_gate_sample.keys = O.OracleKeys(SEED)

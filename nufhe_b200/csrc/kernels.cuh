@@ -295,22 +295,21 @@ __global__ void __launch_bounds__(BR2_THREADS, 1) blind_rotate_kernel(BlindRotat
 //
 // The reference gathers one 2000-byte key row per (ciphertext, j, k) from global memory: ~12 MB of key
 // per ciphertext.  Here a CTA owns a tile of up to KS_TILE ciphertexts and streams the key ONCE per tile:
-// a producer warp moves the three non-zero rows of each (j, k) into a ring of shared-memory stages with
-// cp.async.bulk (TMA, completion on an mbarrier); 8 consumer warps (thread t owns output coefficients
-// 2t, 2t+1 of every ciphertext of the tile) pick the row with the warp-uniform 2-bit digit and subtract.
-// Stage rows are 2048 bytes apart and row 0 of every stage is a permanent zero row (the key's d = 0 row
-// is zero padding, lwe_cpu.py:31-33), so "digit -> byte offset" is one shift and the address is one LOP3:
-// 2.5 instructions per (ciphertext, j, k, coefficient).
+// a producer warp moves the key, 32 000 contiguous bytes (four values of k, all four rows) at a time,
+// into a ring of four shared-memory slots with cp.async.bulk (TMA, completion on an mbarrier); 8 consumer
+// warps (thread t owns output coefficients 2t, 2t+1 of every ciphertext of the tile) pick the row with the
+// warp-uniform 2-bit digit and subtract: 3 instructions per (ciphertext, j, k, coefficient).
+// Row d = 0 of the key is zero padding (lwe_cpu.py:31-33; the reference kernel skips it, its NumPy closure
+// subtracts it): it is streamed like the other rows, so d = 0 needs no branch.
 // src = src1 (+ src2) (+ (0, c)) lets gate_mux fold `(0,1/8) + u1 + u2` (gates.py:657-664) into the load.
 constexpr int KS_TILE = 32;                 // ciphertexts per CTA (run-time tile <= KS_TILE)
-constexpr int KS_CONSUMERS = 256;           // threads 0..249: a[2t], a[2t+1]; thread 250: b and variance
-constexpr int KS_THREADS = KS_CONSUMERS + 32;
-constexpr int KS_STAGES = 8;                // == t, so that stage == k at compile time
-constexpr int KS_ROW_BYTES = 2048;
-constexpr int KS_STAGE_BYTES = 4 * KS_ROW_BYTES;
+constexpr int KS_CONSUMERS = 256;           // threads 0..249: a[2t], a[2t+1] of every ciphertext of the tile
+constexpr int KS_THREADS = KS_CONSUMERS + 64;   // + producer warp (TMA issue) + b/variance warp
+constexpr int KS_SLOTS = 4;                 // ring of half-j slots (4 values of k each): two j in flight
 constexpr int KS_IN = 1024, KS_N = 500;     // fast-path sizes (api_low_level.py:49-50)
-// + KS_STAGE_BYTES of slack: the stage ring is aligned to 8192 bytes so that the row offset can be OR-ed in
-constexpr size_t KS_SMEM_BYTES = (size_t)(KS_STAGES + 1) * KS_STAGE_BYTES + (size_t)KS_IN * KS_TILE * 2 + 2 * KS_STAGES * 8 + 16;
+constexpr int KS_ROW_BYTES = KS_N * 4;
+constexpr int KS_SLOT_BYTES = 4 * 4 * KS_ROW_BYTES;   // 4 k x 4 rows
+constexpr size_t KS_SMEM_BYTES = (size_t)KS_SLOTS * KS_SLOT_BYTES + (size_t)KS_IN * KS_TILE * 2 + 2 * KS_SLOTS * 8 + 128;
 
 struct KeyswitchArgs {
     const i32 *src1_a, *src1_b, *src2_a, *src2_b;   // (B, in), (B,)
@@ -351,22 +350,20 @@ NB_D void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar)
 __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *stages = smem_raw + ((KS_STAGE_BYTES - (smem_u32(smem_raw) & (KS_STAGE_BYTES - 1))) & (KS_STAGE_BYTES - 1));
-    unsigned short *digits = reinterpret_cast<unsigned short *>(stages + KS_STAGES * KS_STAGE_BYTES);  // [j][KS_TILE]
-    u64 *full = reinterpret_cast<u64 *>(stages + KS_STAGES * KS_STAGE_BYTES + KS_IN * KS_TILE * 2);
-    u64 *empty = full + KS_STAGES;
+    unsigned char *ring = smem_raw;                                               // [slot][k & 3][row][2000 B]
+    unsigned short *digits = reinterpret_cast<unsigned short *>(ring + KS_SLOTS * KS_SLOT_BYTES);  // [j][KS_TILE]
+    u64 *full = reinterpret_cast<u64 *>(ring + KS_SLOTS * KS_SLOT_BYTES + KS_IN * KS_TILE * 2);
+    u64 *empty = full + KS_SLOTS;
 
     const int tid = threadIdx.x;
     const size_t ct0 = (size_t)blockIdx.x * p.tile;
     const int nct = (int)min((size_t)p.tile, p.batch - ct0);
 
     if (tid == 0) {
-        for (int s = 0; s < KS_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], KS_CONSUMERS / 32); }
+        for (int s = 0; s < KS_SLOTS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], KS_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // zero rows (row 0 of every stage) and the packed digits of the tile
-    for (int e = tid; e < KS_STAGES * (KS_ROW_BYTES / 4); e += KS_THREADS)
-        reinterpret_cast<u32 *>(stages + (e / (KS_ROW_BYTES / 4)) * KS_STAGE_BYTES)[e % (KS_ROW_BYTES / 4)] = 0;
+    // packed digits of the tile: the 8 two-bit digits of coefficient j of ciphertext q in 16 bits
     const u32 prec_offset = 1u << (32 - (1 + 2 * 8));
     for (int idx = tid; idx < KS_TILE * KS_IN; idx += KS_THREADS) {
         const int q = idx / KS_IN, j = idx % KS_IN;
@@ -374,27 +371,48 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
         if (q < nct) {
             v = (u32)p.src1_a[(ct0 + q) * KS_IN + j];
             if (p.src2_a) v += (u32)p.src2_a[(ct0 + q) * KS_IN + j];
-            v = (v + prec_offset) >> 16;              // the 8 two-bit digits, k = 0 in the top bits
+            v = (v + prec_offset) >> 16;              // k = 0 in the top bits
         }
-        digits[j * KS_TILE + q] = (unsigned short)v;  // ciphertexts beyond nct: all digits 0 -> zero row
+        digits[j * KS_TILE + q] = (unsigned short)v;  // ciphertexts beyond nct: digits 0 (results not stored)
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
+    if (tid >= KS_CONSUMERS + 32) {
+        // ---- b / variance warp: lane q owns ciphertext q of the tile; the 16-byte (j, k) entries of ks_b and
+        // ks_cv are warp-uniform loads.  Runs beside the consumers and never touches the ring.
+        const int q = tid - (KS_CONSUMERS + 32);
+        u32 accb = 0;
+        float cv = 0.f;
+        int4 kb = __ldg(reinterpret_cast<const int4 *>(p.ks_b));
+        float4 kc = __ldg(reinterpret_cast<const float4 *>(p.ks_cv));
+        for (int jk = 0; jk < KS_IN * 8; jk++) {
+            const int4 kb_next = __ldg(reinterpret_cast<const int4 *>(p.ks_b) + min(jk + 1, KS_IN * 8 - 1));
+            const float4 kc_next = __ldg(reinterpret_cast<const float4 *>(p.ks_cv) + min(jk + 1, KS_IN * 8 - 1));
+            const u32 bits = digits[(jk >> 3) * KS_TILE + q];
+            const u32 d = (bits >> (14 - 2 * (jk & 7))) & 3u;
+            accb -= d == 0 ? (u32)kb.x : d == 1 ? (u32)kb.y : d == 2 ? (u32)kb.z : (u32)kb.w;
+            cv += d == 0 ? kc.x : d == 1 ? kc.y : d == 2 ? kc.z : kc.w;
+            kb = kb_next; kc = kc_next;
+        }
+        if (q < nct) {
+            u32 b = (u32)p.src1_b[ct0 + q] + (p.src2_b ? (u32)p.src2_b[ct0 + q] : 0u) + (u32)p.c;
+            p.res_b[ct0 + q] = (i32)(b + accb);
+            if (p.res_cv) p.res_cv[ct0 + q] = cv;
+        }
+        return;
+    }
     if (tid >= KS_CONSUMERS) {
-        // ---- producer warp: one lane streams rows d = 1..3 of (j, k) into stage k ----------------
+        // ---- producer warp: one lane streams the key, 32 000 bytes per slot ------------------------
         if (tid == KS_CONSUMERS) {
             for (int j = 0; j < KS_IN; j++) {
-                const u32 parity = (j & 1) ^ 1;
+                const u32 parity = ((j >> 1) & 1) ^ 1;
 #pragma unroll 1
-                for (int k = 0; k < KS_STAGES; k++) {
-                    mbar_wait(&empty[k], parity);     // first pass: passes immediately (phase -1 "complete")
-                    mbar_expect_tx(&full[k], 3 * KS_N * 4);
-                    const i32 *src = p.ks_a + ((size_t)(j * 8 + k) * 4 + 1) * KS_N;
-                    unsigned char *dst = stages + k * KS_STAGE_BYTES;
-#pragma unroll
-                    for (int d = 1; d < 4; d++)
-                        bulk_g2s(dst + d * KS_ROW_BYTES, src + (d - 1) * KS_N, KS_N * 4, &full[k]);
+                for (int h = 0; h < 2; h++) {
+                    const int slot = 2 * (j & 1) + h;
+                    mbar_wait(&empty[slot], parity);  // first pass: passes immediately (phase -1 "complete")
+                    mbar_expect_tx(&full[slot], KS_SLOT_BYTES);
+                    bulk_g2s(ring + slot * KS_SLOT_BYTES, p.ks_a + (size_t)(j * 8 + 4 * h) * 4 * KS_N, KS_SLOT_BYTES,
+                             &full[slot]);
                 }
             }
         }
@@ -402,19 +420,17 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
     }
 
     // ---- consumers -------------------------------------------------------------------------------
-    const bool is_a = tid < KS_N / 2, is_b = tid == KS_N / 2;
+    const bool is_a = tid < KS_N / 2;
     const int lane = tid & 31;
     u32 acc0[KS_TILE], acc1[KS_TILE];
 #pragma unroll
     for (int q = 0; q < KS_TILE; q++) { acc0[q] = 0; acc1[q] = 0; }
-    // thread 250 (the b column) keeps the float32 variance sums in acc1 (bit patterns)
-    // byte offset of this thread's pair inside a stage row; idle threads read the zero row harmlessly
+    // byte offset of this thread's pair inside a key row; idle threads read pair 0 harmlessly
     const u32 col_off = is_a ? (u32)tid * 8u : 0u;
-    const u32 stage_base = smem_u32(stages);
+    const u32 ring_base = smem_u32(ring);
 
     for (int j = 0; j < KS_IN; j++) {
-        // packed digits of the tile for this j: KS_TILE x u16 = 64 bytes
-        u32 w[KS_TILE / 2];
+        u32 w[KS_TILE / 2];                            // packed digits of the tile for this j (64 bytes)
         {
             const uint4 *dg = reinterpret_cast<const uint4 *>(digits + j * KS_TILE);
 #pragma unroll
@@ -423,36 +439,27 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
                 w[4 * x] = t.x; w[4 * x + 1] = t.y; w[4 * x + 2] = t.z; w[4 * x + 3] = t.w;
             }
         }
-        const u32 parity = j & 1;
+        const u32 parity = (j >> 1) & 1;
+        const u32 jbase = ring_base + (j & 1) * (2 * KS_SLOT_BYTES) + col_off;
 #pragma unroll
-        for (int k = 0; k < KS_STAGES; k++) {
-            mbar_wait(&full[k], parity);
-            const u32 base = stage_base + k * KS_STAGE_BYTES + col_off;
-            if (is_b) {
-                const int4 kb = __ldg(reinterpret_cast<const int4 *>(p.ks_b + (size_t)(j * 8 + k) * 4));
-                const float4 kc = __ldg(reinterpret_cast<const float4 *>(p.ks_cv + (size_t)(j * 8 + k) * 4));
+        for (int k = 0; k < 8; k++) {
+            if ((k & 3) == 0) mbar_wait(&full[2 * (j & 1) + (k >> 2)], parity);
+            const u32 base = jbase + k * (4 * KS_ROW_BYTES);
+            {
 #pragma unroll
                 for (int q = 0; q < KS_TILE; q++) {
                     const u32 d = (w[q >> 1] >> (16 * (q & 1) + 14 - 2 * k)) & 3u;
-                    acc0[q] -= d == 1 ? (u32)kb.y : d == 2 ? (u32)kb.z : d == 3 ? (u32)kb.w : 0u;
-                    const float c = d == 1 ? kc.y : d == 2 ? kc.z : d == 3 ? kc.w : 0.f;
-                    acc1[q] = __float_as_uint(__uint_as_float(acc1[q]) + c);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < KS_TILE; q++) {
-                    // digit (2 bits) moved to bits 11..12 = row * 2048
-                    const int pos = 16 * (q & 1) + 14 - 2 * k;          // bit position of the digit
-                    const u32 sh = pos >= 11 ? (w[q >> 1] >> (pos - 11)) : (w[q >> 1] << (11 - pos));
-                    const u32 addr = (sh & 0x1800u) | base;            // base has bits 11..12 clear
+                    const u32 addr = d * (u32)KS_ROW_BYTES + base;
                     u32 v0, v1;
                     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(addr));
                     acc0[q] -= v0;
                     acc1[q] -= v1;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[k]);
+            if ((k & 3) == 3) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[2 * (j & 1) + (k >> 2)]);
+            }
         }
     }
 
@@ -462,10 +469,6 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
             if (is_a) {
                 p.res_a[(ct0 + q) * KS_N + 2 * tid] = (i32)acc0[q];
                 p.res_a[(ct0 + q) * KS_N + 2 * tid + 1] = (i32)acc1[q];
-            } else if (is_b) {
-                u32 b = (u32)p.src1_b[ct0 + q] + (p.src2_b ? (u32)p.src2_b[ct0 + q] : 0u) + (u32)p.c;
-                p.res_b[ct0 + q] = (i32)(b + acc0[q]);
-                if (p.res_cv) p.res_cv[ct0 + q] = __uint_as_float(acc1[q]);
             }
         }
     }
@@ -489,7 +492,6 @@ __global__ void __launch_bounds__(512) keyswitch_generic_kernel(KeyswitchArgs p)
         const i32 tmp = (i32)(v + prec_offset);
         for (int k = 0; k < p.t; k++) {
             const int d = (tmp >> (32 - (k + 1) * p.log2_base)) & (base - 1);
-            if (d == 0) continue;                    // zero padding row (lwe_gpu.mako:97-106)
             const size_t row = ((size_t)j * p.t + k) * base + d;
             if (is_a) acc -= (u32)__ldg(p.ks_a + row * p.n + i);
             else { acc -= (u32)__ldg(p.ks_b + row); cv += __ldg(p.ks_cv + row); }

@@ -116,6 +116,15 @@ static void init_tables(void)
 }
 void orc_init(void) { init_tables(); }
 
+#ifdef _OPENMP
+#include <omp.h>
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_get_threads(void) { return omp_get_max_threads(); }
+#else
+void orc_set_threads(int n) { (void)n; }
+int orc_get_threads(void) { return 1; }
+#endif
+
 /* returns 0 when the folded reduction agrees with the plain `% p` on edge values and n random pairs */
 int orc_selftest(u64 seed, size_t n)
 {

@@ -50,6 +50,15 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """Number of OpenMP threads the C oracle uses (bench.py sets it to the usable host cores)."""
+    lib().orc_set_threads(ctypes.c_int(int(n)))
+
+
+def get_threads():
+    return int(lib().orc_get_threads())
+
+
 def _p(arr):
     return arr.ctypes.data_as(ctypes.c_void_p)
 
