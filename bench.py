@@ -307,8 +307,8 @@ def run_b200_arm(args):
         ms_per_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total * 1e-3)
         e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-        h2d = n_ops * (B * LWE_N * 4 + B * 4)
-        d2h = B * LWE_N * 4 + B * 4
+        h2d = world * n_ops * (B * LWE_N * 4 + B * 4)     # whole job, all ranks
+        d2h = world * (B * LWE_N * 4 + B * 4)
         line = {
             'metric': metric_name(args), 'value': value, 'unit': 'gates/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
