@@ -58,6 +58,7 @@ int nb_ntt_inverse_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
 #define NB_FF_MUL_PREPARED 3 /* a*b*2^-64, arithmetic.mako:355-419 */
 #define NB_FF_PREPARE 4      /* a*2^64,    arithmetic.mako:336-352 */
 #define NB_FF_LSH 5          /* a*2^b, b < 192, arithmetic.mako:465-1045 */
+#define NB_FF_LSH_CONST 6    /* same result through the compile-time-shift code paths the transforms use */
 int nb_ff_elementwise(nb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n,
                       size_t b_period);
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('NUFHE_B200_LIB') or os.path.join(_HERE, 'csrc', 'libnufhe_b200.so')
 
 NB_OK, NB_EINVAL, NB_EUNSUPPORTED, NB_ECUDA = 0, -1, -2, -3
-FF_ADD, FF_SUB, FF_MUL, FF_MUL_PREPARED, FF_PREPARE, FF_LSH = range(6)
+FF_ADD, FF_SUB, FF_MUL, FF_MUL_PREPARED, FF_PREPARE, FF_LSH, FF_LSH_CONST = range(7)
 
 _vp = ctypes.c_void_p
 _sz = ctypes.c_size_t

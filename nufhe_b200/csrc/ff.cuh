@@ -88,7 +88,9 @@ NB_HD u64 ff_add(u64 a, u64 b) { return ff_sub(a, FF_P - b); }
 NB_HD u64 ff_eps_mul(u32 v)
 {
 #if defined(__CUDA_ARCH__)
-    return (u64)v * (u64)nb_c_eps;
+    u64 t;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(v), "r"(nb_c_eps));
+    return t;
 #else
     return ((u64)v << 32) - v;
 #endif
@@ -105,10 +107,59 @@ NB_HD u64 ff_reduce128(u64 lo, u64 hi)
     return ff_canon(r);
 }
 
+#if defined(__CUDA_ARCH__)
+// 64 x 64 -> 128 bit product as four 32-bit limbs: 4 IMAD.WIDE + 6 carry-chain adds
+NB_D void mul128(u64 a, u64 b, u32 &l, u32 &m, u32 &h0, u32 &h1)
+{
+    u64 p00, p01, p10, p11;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p00) : "r"(lo32(a)), "r"(lo32(b)));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p01) : "r"(lo32(a)), "r"(hi32(b)));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p10) : "r"(hi32(a)), "r"(lo32(b)));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p11) : "r"(hi32(a)), "r"(hi32(b)));
+    l = lo32(p00);
+    asm("add.cc.u32 %0, %3, %4;\n\t"
+        "addc.cc.u32 %1, %5, %6;\n\t"
+        "addc.u32 %2, %7, 0;\n\t"
+        "add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "=&r"(m), "=&r"(h0), "=&r"(h1)
+        : "r"(hi32(p00)), "r"(lo32(p01)), "r"(hi32(p01)), "r"(lo32(p11)), "r"(hi32(p11)), "r"(lo32(p10)),
+          "r"(hi32(p10)));
+}
+// l + m phi + h0 phi^2 + h1 phi^3 -> canonical: (m:l) - h1 (borrow fixed), + h0 * eps (carry fixed), canon
+NB_D u64 ff_reduce_limbs(u32 l, u32 m, u32 h0, u32 h1)
+{
+    u32 u0, u1, r0, r1, k;
+    {
+        u64 t;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(h0), "r"(nb_c_eps));
+        u0 = lo32(t); u1 = hi32(t);
+    }
+    asm("sub.cc.u32 %0, %3, %5;\n\t"
+        "subc.cc.u32 %1, %4, 0;\n\t"
+        "subc.u32 %2, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, %2;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "add.cc.u32 %0, %0, %6;\n\t"
+        "addc.cc.u32 %1, %1, %7;\n\t"
+        "addc.u32 %2, 0, 0;\n\t"            // carry as 0/1 (an add-chain flag must be read by addc: ptxas keeps
+        "sub.cc.u32 %0, %0, %2;\n\t"        // subtraction borrows in the inverted sense, so never mix the two)
+        "subc.u32 %1, %1, 0;\n\t"           // + carry * eps = - carry + carry * 2^32
+        "add.u32 %1, %1, %2;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(k)
+        : "r"(l), "r"(m), "r"(h1), "r"(u0), "r"(u1));
+    const bool ge = r1 == 0xffffffffu && r0 != 0u;
+    return ge ? (u64)(r0 - 1u) : pack(r0, r1);
+}
+#endif
+
 NB_HD u64 ff_mul(u64 a, u64 b)
 {
 #if defined(__CUDA_ARCH__)
-    return ff_reduce128(a * b, __umul64hi(a, b));
+    u32 l, m, h0, h1;
+    mul128(a, b, l, m, h0, h1);
+    return ff_reduce_limbs(l, m, h0, h1);
 #else
     unsigned __int128 pr = (unsigned __int128)a * b;
     return ff_reduce128((u64)pr, (u64)(pr >> 64));
@@ -188,10 +239,12 @@ NB_HD Limbs3 ff_bitshift(u64 x, int r)     // r in [0, 32)
     u32 x0 = lo32(x), x1 = hi32(x);
 #if defined(__CUDA_ARCH__)
     {
+        // two IMAD.WIDE (FMA pipe) and one OR: the carry-in bits of the middle limb never overlap
         const u32 k = nb_c_pow2[r];
-        u64 t = (u64)x0 * (u64)k;
-        u64 u = (u64)x1 * (u64)k + (u64)hi32(t);
-        y.y0 = lo32(t); y.y1 = lo32(u); y.y2 = hi32(u);
+        u64 t, u;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(x0), "r"(k));
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(u) : "r"(x1), "r"(k));
+        y.y0 = lo32(t); y.y1 = lo32(u) | hi32(t); y.y2 = hi32(u);
         return y;
     }
 #endif
@@ -221,15 +274,105 @@ NB_HD u64 ff_limbs_combine(Limbs3 y, int q, bool negate)
     return negate ? ff_sub(neg, pos) : ff_sub(pos, neg);
 }
 
-// x * 2^S mod p, S a compile-time constant (any non-negative integer; reduced mod 192)
+#if defined(__CUDA_ARCH__)
+// ---- device-only tight forms of the six (q, sign) limb combinations ------------------------------
+// Inputs: y = x << r as limbs (y2 < 2^31).  Outputs are in [0, p] ("almost canonical": p itself may
+// stand for 0; ff_sub / ff_add / ff_mul / the shifts are closed over that range and ff_to_i32(p) = 0).
+NB_D void mulwide(u32 a, u32 b, u32 &lo, u32 &hi)
+{
+    u64 t;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
+    lo = lo32(t); hi = hi32(t);
+}
+// w + u mod p for w any 64-bit value and u < 2^63 + 2^32: one conditional subtraction of p
+NB_D u64 ff_add_loose_small(u32 w0, u32 w1, u32 u0, u32 u1)
+{
+    u32 r0, r1, t0, t1, k;
+    asm("add.cc.u32 %0, %5, %7;\n\t"
+        "addc.cc.u32 %1, %6, %8;\n\t"
+        "addc.u32 %4, 0, 0;\n\t"
+        "add.cc.u32 %2, %0, 0xffffffff;\n\t"
+        "addc.cc.u32 %3, %1, 0;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(t0), "=&r"(t1), "=&r"(k)
+        : "r"(w0), "r"(w1), "r"(u0), "r"(u1));
+    return k ? pack(t0, t1) : pack(r0, r1);
+}
+// pattern a: (y0 - y2) + (y1 + y2) phi = pack(y0, y1) + y2 * eps
+NB_D u64 ff_comb_a(u32 y0, u32 y1, u32 y2)
+{
+    u32 u0, u1;
+    mulwide(y2, nb_c_eps, u0, u1);
+    return ff_add_loose_small(y0, y1, u0, u1);
+}
+// pattern b: (-y1 - y2) + (y0 + y1) phi = y0 * 2^32 + y1 * eps - y2
+NB_D u64 ff_comb_b(u32 y0, u32 y1, u32 y2)
+{
+    u32 u0, u1, lo, hi, k, ks;
+    mulwide(y1, nb_c_eps, u0, u1);
+    asm("add.cc.u32 %1, %4, %5;\n\t"        // hi = u1 + y0
+        "addc.u32 %2, 0, 0;\n\t"            // k = carry
+        "sub.cc.u32 %0, %3, %6;\n\t"        // lo = u0 - y2
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 %2, %2, 0;"                 // k in {-1, 0, 1}; -1 only when y0 = y1 = 0 < y2
+        : "=&r"(lo), "=&r"(hi), "=&r"(k)
+        : "r"(u0), "r"(u1), "r"(y0), "r"(y2));
+    // fold k * 2^64 = k * eps: (hi:lo) - k + k * 2^32 (two's complement k)
+    ks = (u32)((i32)k >> 31);
+    asm("sub.cc.u32 %0, %0, %2;\n\t"
+        "subc.u32 %1, %1, %3;\n\t"
+        "add.u32 %1, %1, %2;"
+        : "+r"(lo), "+r"(hi) : "r"(k), "r"(ks));
+    // k = +-1 leaves a canonical value; k = 0 may leave [p, 2^64)
+    const bool ge = hi == 0xffffffffu && lo != 0u;
+    return ge ? (u64)(lo - 1u) : pack(lo, hi);
+}
+// pattern c: (-y0 - y1) + (y0 - y2) phi = y0 * eps - pack(y1, y2);  pack(y1, y2) < 2^63
+NB_D u64 ff_comb_c(u32 y0, u32 y1, u32 y2)
+{
+    u32 u0, u1;
+    mulwide(y0, nb_c_eps, u0, u1);
+    return ff_sub(pack(u0, u1), pack(y1, y2));
+}
+NB_D u64 ff_comb_c_neg(u32 y0, u32 y1, u32 y2)
+{
+    u32 u0, u1;
+    mulwide(y0, nb_c_eps, u0, u1);
+    return ff_sub(pack(y1, y2), pack(u0, u1));
+}
+template <int S> NB_D u64 ff_shl_dev(u64 x)
+{
+    constexpr int s = S % 192, s96 = s % 96, r = s96 % 32, q = s96 / 32;
+    constexpr bool negate = s >= 96;
+    u32 y0, y1, y2;
+    if (r == 0) { y0 = lo32(x); y1 = hi32(x); y2 = 0; }
+    else {
+        u32 c, z;
+        mulwide(lo32(x), nb_c_pow2[r], y0, c);
+        mulwide(hi32(x), nb_c_pow2[r], z, y2);
+        y1 = z | c;
+    }
+    if (q == 0) { u64 v = ff_comb_a(y0, y1, y2); return negate ? FF_P - v : v; }
+    if (q == 1) { u64 v = ff_comb_b(y0, y1, y2); return negate ? FF_P - v : v; }
+    return negate ? ff_comb_c_neg(y0, y1, y2) : ff_comb_c(y0, y1, y2);
+}
+#endif
+
+// x * 2^S mod p, S a compile-time constant (any non-negative integer; reduced mod 192).
+// Host: canonical in, canonical out.  Device: [0, p] in, [0, p] out (see above).
 template <int S> NB_HD u64 ff_shl(u64 x)
 {
     constexpr int s = S % 192;
     constexpr int s96 = s % 96;
     constexpr bool negate = s >= 96;
     if (s == 0) return x;
+#if defined(__CUDA_ARCH__)
+    if (s == 96) return FF_P - x;
+    return ff_shl_dev<S>(x);
+#else
     if (s == 96) return ff_neg(x);
     return ff_limbs_combine(ff_bitshift(x, s96 % 32), s96 / 32, negate);
+#endif
 }
 
 // x * 2^s mod p for a run-time s in [0, 192)

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) ntt_forward_kernel(const void *__restrict
         warp_ntt_forward(v, scratch, twd, lane);
         if (live) {
 #pragma unroll
-            for (int s = 0; s < 32; s++) out[p * NTT_N + ntt_out_index(lane, s)] = v[s];
+            for (int s = 0; s < 32; s++) out[p * NTT_N + ntt_out_index(lane, s)] = ff_canon(v[s]);
         }
     }
 }
@@ -102,14 +102,15 @@ __global__ void __launch_bounds__(128) ntt_inverse_kernel(const u64 *__restrict_
             for (int s = 0; s < 32; s++) {
                 size_t idx = p * NTT_N + ntt_in_index(lane, s);
                 if (OUT_I32) ((i32 *)out)[idx] = ff_to_i32(v[s]);
-                else ((u64 *)out)[idx] = v[s];
+                else ((u64 *)out)[idx] = ff_canon(v[s]);
             }
         }
     }
 }
 
 // ---- element-wise field ops (unit tests of the arithmetic; key generation) ----------------------
-enum FfOp { FF_OP_ADD = 0, FF_OP_SUB = 1, FF_OP_MUL = 2, FF_OP_MUL_PREPARED = 3, FF_OP_PREPARE = 4, FF_OP_LSH = 5 };
+enum FfOp { FF_OP_ADD = 0, FF_OP_SUB = 1, FF_OP_MUL = 2, FF_OP_MUL_PREPARED = 3, FF_OP_PREPARE = 4, FF_OP_LSH = 5,
+            FF_OP_LSH_CONST = 6 };   // 6: the compile-time-shift code paths of the transforms, for unit tests
 
 __global__ void ff_elementwise_kernel(int op, const u64 *__restrict__ a, const u64 *__restrict__ b,
                                       u64 *__restrict__ out, size_t n, size_t b_period)
@@ -124,9 +125,15 @@ __global__ void ff_elementwise_kernel(int op, const u64 *__restrict__ a, const u
         case FF_OP_MUL: r = ff_mul(x, ff_canon(y)); break;
         case FF_OP_MUL_PREPARED: r = ff_mul_prepared(x, ff_canon(y)); break;
         case FF_OP_PREPARE: r = ff_prepare_for_mul(x); break;
+        case FF_OP_LSH_CONST: {
+            const int sh = (int)(y % 192);
+            r = x;
+            static_for<0, 192>([&](auto S) { if (sh == decltype(S)::value) r = ff_shl<decltype(S)::value>(x); });
+            break;
+        }
         default: r = ff_shl_var(x, (int)(y % 192)); break;
         }
-        out[i] = r;
+        out[i] = ff_canon(r);
     }
 }
 

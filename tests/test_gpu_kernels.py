@@ -31,6 +31,22 @@ def test_arithmetic(eng, golden):
     assert (eng.to_host(eng.ff_op(nv.FF_PREPARE, da), True) == g['prepare_for_mul']).all()
     ds = dev_u64(eng, s.astype(numpy.uint64))
     assert (eng.to_host(eng.ff_op(nv.FF_LSH, da, ds), True) == g['lsh']).all()
+    assert (eng.to_host(eng.ff_op(nv.FF_LSH_CONST, da, ds), True) == g['lsh']).all()
+
+
+def test_constant_shift_paths_exhaustive(eng):
+    """Every compile-time shift 0..191 used by the transforms, on edge values (incl. the non-canonical
+    representative p of zero that the device arithmetic tolerates) and random field elements."""
+    from nufhe_b200 import _native as nv
+    rng = G.rs(21)
+    edge = numpy.concatenate([G.FF_EDGE, numpy.array([G.P, 2**64 - 1, 2**63 - 1, 0xffffffff00000000,
+                                                      0xfffffffeffffffff, 0x00000000ffffffff], numpy.uint64)])
+    vals = numpy.concatenate([edge, G.ff_numbers(rng, (256 - edge.size,))])
+    a = numpy.repeat(vals, 192)
+    s = numpy.tile(numpy.arange(192, dtype=numpy.uint64), vals.size)
+    got = eng.to_host(eng.ff_op(nv.FF_LSH_CONST, dev_u64(eng, a), dev_u64(eng, s)), True)
+    want = O.ff_lsh(a, s.astype(numpy.uint32))
+    assert (got == want).all()
 
 
 def test_arithmetic_random_vs_oracle(eng):
