@@ -28,8 +28,12 @@
 
 namespace nb {
 
-constexpr int BR2_CT = 4;                         // ciphertexts per CTA
-constexpr int BR2_THREADS = 512;
+#ifndef NB_BR_CT
+#define NB_BR_CT 2
+#endif
+constexpr int BR2_CT = NB_BR_CT;                  // ciphertexts per CTA (1, 2 or 4)
+constexpr int BR2_THREADS = 128 * BR2_CT;         // 128 threads per ciphertext: every pass is 1 or 2 full sweeps
+constexpr int BR2_CTAS_PER_SM = 4 / BR2_CT;       // 16 warps per SM either way
 constexpr int ROW_STRIDE = 66;                    // u64 per row (64 + 2 padding)
 constexpr int POLY_STRIDE = 16 * ROW_STRIDE;      // u64 per work polynomial
 constexpr int BR2_POLYS = 4 * BR2_CT;             // work polynomials per CTA
@@ -236,7 +240,7 @@ NB_HD void phase_inv3(int p, int row, int u, u64 *w_all)
 // ---- MAC: thread = (row, pair q): stored columns 2q, 2q+1 of every work polynomial -----------------
 // bk_row: internal layout [mi][j][mo][row * 64 + stored column], plain (non-Montgomery) values.
 // out polynomial mo of ciphertext ct overwrites work polynomial ct*4 + mo.
-NB_HD void phase_mac(int row, int q, u64 *w_all, const u64 *bk_row)
+NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64 *bk_row)
 {
     const int pos = row * 64 + 2 * q;
     u64 bk[BK_PLANES][2];
@@ -265,6 +269,12 @@ NB_HD void phase_mac(int row, int q, u64 *w_all, const u64 *bk_row)
     }
 }
 
+// all 16 rows x 32 pairs, BR2_THREADS threads
+NB_HD void phase_mac(int tid, u64 *w_all, const u64 *bk_row)
+{
+    for (int row = tid >> 5; row < 16; row += BR2_THREADS / 32) phase_mac_row(row, tid & 31, w_all, bk_row);
+}
+
 // ---- inv1: task = (ct, mo, j2): reads W[ct*4+mo], writes ACC[ct][mo] --------------------------------
 // twd_inv: [row][j2] = psi^-(j2 (2 k1 + 1)) / 1024.  ACCUMULATE: acc += result, else acc = result.
 template <bool ACCUMULATE>
@@ -291,19 +301,21 @@ NB_HD void phase_inv1(int task, i32 *acc_all, const u64 *w_all, const u64 *twd_i
 // thread -> task maps (tid in [0, 512), it = iteration)
 NB_HD void map_fwd2(int tid, int it, int &p, int &row, int &g)
 {
-    g = tid >> 7;                                      // warp-uniform
-    int x = it * 128 + (tid & 127);
+    constexpr int Q = BR2_THREADS / 4;                 // threads per value of g (>= 32: g is warp-uniform)
+    g = tid / Q;
+    int x = it * Q + (tid % Q);
     p = x >> 4; row = x & 15;
 }
 NB_HD void map_fwd3(int tid, int it, int &p, int &row, int &u)
 {
-    u = tid & 3; row = (tid >> 2) & 15; p = it * 8 + (tid >> 6);
+    u = tid & 3; row = (tid >> 2) & 15; p = it * (BR2_THREADS / 64) + (tid >> 6);
 }
-// inverse passes act on polynomials ct*4 + mo only (8 of the 16)
+// inverse passes act on polynomials ct*4 + mo only (half of the work polynomials)
 NB_HD void map_inv2(int tid, int &p, int &row, int &g)
 {
-    g = tid >> 7;
-    int x = tid & 127;                                 // 8 polys x 16 rows
+    constexpr int Q = BR2_THREADS / 4;
+    g = tid / Q;
+    int x = tid % Q;                                   // 2 CT polys x 16 rows
     int pp = x >> 4; row = x & 15;
     p = (pp >> 1) * 4 + (pp & 1);
 }

@@ -1,5 +1,6 @@
 // capi.cu -- the C ABI of libnufhe_b200.so (see include/nufhe_b200.h).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include "../../include/nufhe_b200.h"
@@ -15,6 +16,7 @@ struct nb_ctx {
     u64 *d_ph_fwd, *d_ph_inv;            // phase tables (fused bootstrap)
     u64 *d_ones512;                      // 512 * NTT(all-ones), natural order (bk_prepare)
     int sm_count;
+    int stagger_cycles;
     std::string err;
 };
 
@@ -53,6 +55,10 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     cudaDeviceProp prop;
     NB_TRY(check(ctx, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"));
     ctx->sm_count = prop.multiProcessorCount;
+    {
+        const char *e = getenv("NUFHE_B200_STAGGER");     // developer knob (cycles); measured: no effect, default off
+        ctx->stagger_cycles = e ? atoi(e) : 0;
+    }
     if (prop.major < 10)
         return fail(ctx, NB_EUNSUPPORTED, "libnufhe_b200 is built for sm_100a only; device is sm_" +
                                               std::to_string(prop.major) + std::to_string(prop.minor));
@@ -200,7 +206,7 @@ int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, siz
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
     BlindRotateArgs p{};
     p.accum = accum; p.accum_out = accum; p.bk = (const u64 *)bk_int + bk_row * BK_ROW_U64;
-    p.plain = 1; p.batch = batch;
+    p.plain = 1; p.batch = batch; p.sm_count = ctx->sm_count; p.stagger_cycles = 0;
     int grid = (int)((batch + BR2_CT - 1) / BR2_CT);
     blind_rotate_kernel<<<grid, BR2_THREADS, BR2_SMEM_BYTES, ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);
     return launch_check(ctx, "blind_rotate_kernel(plain external product)");
@@ -212,6 +218,8 @@ static int launch_blind_rotate(nb_ctx *ctx, BlindRotateArgs &p)
     if (p.batch == 0) return NB_OK;
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
     int grid = (int)((p.batch + BR2_CT - 1) / BR2_CT);
+    p.sm_count = ctx->sm_count;
+    p.stagger_cycles = ctx->stagger_cycles;
     blind_rotate_kernel<<<grid, BR2_THREADS, BR2_SMEM_BYTES, ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);
     return launch_check(ctx, "blind_rotate_kernel");
 }

@@ -58,6 +58,8 @@ void emul_ntt_inverse(const u64 *in, u64 *out, size_t batch)
 // ciphertexts, phases executed in order with all "threads" of a phase run back to back.
 // acc: (nct, 2, 1024) in/out; bk_ref_row: reference layout (2,2,2,1024) Montgomery; rot: rotation
 // amounts per ciphertext or NULL (plain external product, overwrite).
+int emul_phase_ct(void) { return BR2_CT; }
+
 void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct)
 {
     static PhaseTables T;
@@ -65,7 +67,7 @@ void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct
     std::vector<u64> w(BR2_POLYS * POLY_STRIDE, 0);
     std::vector<u64> bk(BK_ROW_U64);
     for (int c = 0; c < nct; c++) memcpy(&acc[c * 2 * NTT_N], acc_io + c * 2 * NTT_N, sizeof(i32) * 2 * NTT_N);
-    int rots[BR2_CT] = {0, 0, 0, 0};
+    int rots[4] = {0, 0, 0, 0};
     if (rot) for (int c = 0; c < nct; c++) rots[c] = rot[c];
     // bk_prepare: internal [m][row*64 + scol] plain
     for (int pos = 0; pos < NTT_N; pos++) {
@@ -87,7 +89,7 @@ void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct
         for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, g; map_fwd2(tid, it, p, r, g); phase_fwd2(p, r, g, w.data()); }
     for (int it = 0; it < 2; it++)
         for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, u; map_fwd3(tid, it, p, r, u); phase_fwd3(p, r, u, w.data()); }
-    for (int tid = 0; tid < BR2_THREADS; tid++) phase_mac(tid >> 5, tid & 31, w.data(), bk.data());
+    for (int tid = 0; tid < BR2_THREADS; tid++) phase_mac(tid, w.data(), bk.data());
     for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, u; map_inv3(tid, p, r, u); phase_inv3(p, r, u, w.data()); }
     for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, g; map_inv2(tid, p, r, g); phase_inv2(p, r, g, w.data()); }
     for (int tid = 0; tid < BR2_THREADS; tid++) {

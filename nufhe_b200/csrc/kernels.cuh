@@ -184,6 +184,8 @@ struct BlindRotateArgs {
     int n;                  // LWE dimension (500); n = 0 with `plain` = one external product
     int extract;            // write out_a/out_b
     int plain;              // 1: accum <- bk[0] (x) accum, no rotation (tgsw.py:165-172), n ignored
+    int sm_count;           // for the start-up stagger of co-resident CTAs
+    int stagger_cycles;     // ~ half a CMux step; 0 disables
     size_t batch;
 };
 
@@ -228,7 +230,7 @@ NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *
     for (int it = 0; it < 2; it++) { int p, r, u; map_fwd3(tid, it, p, r, u); phase_fwd3(p, r, u, s.w); }
     __syncthreads();
     // multiply-accumulate with the key row (tgsw_gpu.py:58-107); each key element is fetched once per CTA
-    phase_mac(tid >> 5, tid & 31, s.w, bk_row);
+    phase_mac(tid, s.w, bk_row);
     __syncthreads();
     // inverse transforms of the 8 output polynomials
     { int p, r, u; map_inv3(tid, p, r, u); phase_inv3(p, r, u, s.w); }
@@ -238,7 +240,7 @@ NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *
     phase_inv1<ROTATE>(tid, s.acc, s.w, s.twd_inv);
 }
 
-__global__ void __launch_bounds__(BR2_THREADS, 1) blind_rotate_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g,
+__global__ void __launch_bounds__(BR2_THREADS, BR2_CTAS_PER_SM) blind_rotate_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g,
                                                                        const u64 *__restrict__ twd_inv_g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -246,6 +248,17 @@ __global__ void __launch_bounds__(BR2_THREADS, 1) blind_rotate_kernel(BlindRotat
     const int tid = threadIdx.x;
     for (int i = tid; i < NTT_N; i += BR2_THREADS) { s.twd_fwd[i] = twd_fwd_g[i]; s.twd_inv[i] = twd_inv_g[i]; }
 
+    // Two CTAs share an SM (BR2_CTAS_PER_SM).  Optional start-up stagger so that the pair runs out of phase
+    // (MAC is IMAD-heavy, the transform passes IADD3-heavy).  Measured on B200: no gain -- the kernel sits at
+    // the ALU pipe's ceiling either way (profiles/r1_v23_*) -- so ctx->stagger_cycles defaults to 0.
+    if (BR2_CTAS_PER_SM > 1 && p.stagger_cycles > 0 && ((blockIdx.x / p.sm_count) & 1) &&
+        blockIdx.x < (unsigned)(BR2_CTAS_PER_SM * p.sm_count)) {
+        if (tid == 0) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < p.stagger_cycles) { }
+        }
+        __syncthreads();
+    }
     const size_t ct0 = (size_t)blockIdx.x * BR2_CT;
     // ciphertext slots beyond the batch replay the last ciphertext and store nothing
     auto ct_of = [&](int slot) { size_t c = ct0 + slot; return c < p.batch ? c : p.batch - 1; };
