@@ -274,7 +274,17 @@ int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, cons
         if (tile < 1) tile = 1;
         p.tile = (int)tile;
         int grid = (int)((batch + tile - 1) / tile);
-        keyswitch_kernel<<<grid, KS_THREADS, KS_SMEM_BYTES, ctx->stream>>>(p);
+        // small batches: split the 1024 input coefficients over blockIdx.y and accumulate with atomics
+        int splits = ctx->sm_count / grid;
+        if (splits > 32) splits = 32;
+        if (splits < 1) splits = 1;
+        p.splits = splits;
+        if (splits > 1) {
+            NB_TRY(check(ctx, cudaMemsetAsync(res_a, 0, batch * n * sizeof(int32_t), ctx->stream), "cudaMemsetAsync"));
+            NB_TRY(check(ctx, cudaMemsetAsync(res_b, 0, batch * sizeof(int32_t), ctx->stream), "cudaMemsetAsync"));
+            if (res_cv) NB_TRY(check(ctx, cudaMemsetAsync(res_cv, 0, batch * sizeof(float), ctx->stream), "cudaMemsetAsync"));
+        }
+        keyswitch_kernel<<<dim3(grid, splits), KS_THREADS, KS_SMEM_BYTES, ctx->stream>>>(p);
     } else {
         keyswitch_generic_kernel<<<(int)batch, 512, 0, ctx->stream>>>(p);
     }

@@ -340,6 +340,8 @@ struct KeyswitchArgs {
     float *res_cv;                                   // optional
     int in_size, n, t, log2_base;
     int tile;                                        // ciphertexts per CTA (fast path)
+    int splits;                                      // > 1: blockIdx.y takes a slice of j and results are
+                                                     // accumulated with integer atomics into zeroed outputs
     size_t batch;
 };
 
@@ -378,6 +380,12 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
     const int tid = threadIdx.x;
     const size_t ct0 = (size_t)blockIdx.x * p.tile;
     const int nct = (int)min((size_t)p.tile, p.batch - ct0);
+    // slice of the input coefficients handled by this CTA (small batches: split-j over blockIdx.y so that
+    // one ciphertext does not stream the whole 65 MB key through a single SM); always an even number of j
+    const int j_per = ((KS_IN + p.splits - 1) / p.splits + 1) & ~1;
+    const int j_begin = blockIdx.y * j_per;
+    const int j_end = min(KS_IN, j_begin + j_per);
+    const bool split = p.splits > 1;
 
     if (tid == 0) {
         for (int s = 0; s < KS_SLOTS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], KS_CONSUMERS / 32); }
@@ -405,7 +413,9 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
         float cv = 0.f;
         int4 kb = __ldg(reinterpret_cast<const int4 *>(p.ks_b));
         float4 kc = __ldg(reinterpret_cast<const float4 *>(p.ks_cv));
-        for (int jk = 0; jk < KS_IN * 8; jk++) {
+        kb = __ldg(reinterpret_cast<const int4 *>(p.ks_b) + min(j_begin * 8, KS_IN * 8 - 1));
+        kc = __ldg(reinterpret_cast<const float4 *>(p.ks_cv) + min(j_begin * 8, KS_IN * 8 - 1));
+        for (int jk = j_begin * 8; jk < j_end * 8; jk++) {
             const int4 kb_next = __ldg(reinterpret_cast<const int4 *>(p.ks_b) + min(jk + 1, KS_IN * 8 - 1));
             const float4 kc_next = __ldg(reinterpret_cast<const float4 *>(p.ks_cv) + min(jk + 1, KS_IN * 8 - 1));
             const u32 bits = digits[(jk >> 3) * KS_TILE + q];
@@ -416,16 +426,21 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
         }
         if (q < nct) {
             u32 b = (u32)p.src1_b[ct0 + q] + (p.src2_b ? (u32)p.src2_b[ct0 + q] : 0u) + (u32)p.c;
-            p.res_b[ct0 + q] = (i32)(b + accb);
-            if (p.res_cv) p.res_cv[ct0 + q] = cv;
+            if (!split) {
+                p.res_b[ct0 + q] = (i32)(b + accb);
+                if (p.res_cv) p.res_cv[ct0 + q] = cv;
+            } else {
+                atomicAdd(reinterpret_cast<unsigned int *>(p.res_b + ct0 + q), (blockIdx.y == 0 ? b : 0u) + accb);
+                if (p.res_cv) atomicAdd(p.res_cv + ct0 + q, cv);
+            }
         }
         return;
     }
     if (tid >= KS_CONSUMERS) {
         // ---- producer warp: one lane streams the key, 32 000 bytes per slot ------------------------
         if (tid == KS_CONSUMERS) {
-            for (int j = 0; j < KS_IN; j++) {
-                const u32 parity = ((j >> 1) & 1) ^ 1;
+            for (int j = j_begin; j < j_end; j++) {
+                const u32 parity = ((((j - j_begin) >> 1) & 1)) ^ 1;
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {
                     const int slot = 2 * (j & 1) + h;
@@ -449,7 +464,7 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
     const u32 col_off = is_a ? (u32)tid * 8u : 0u;
     const u32 ring_base = smem_u32(ring);
 
-    for (int j = 0; j < KS_IN; j++) {
+    for (int j = j_begin; j < j_end; j++) {
         u32 w[KS_TILE / 2];                            // packed digits of the tile for this j (64 bytes)
         {
             const uint4 *dg = reinterpret_cast<const uint4 *>(digits + j * KS_TILE);
@@ -459,7 +474,7 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
                 w[4 * x] = t.x; w[4 * x + 1] = t.y; w[4 * x + 2] = t.z; w[4 * x + 3] = t.w;
             }
         }
-        const u32 parity = (j >> 1) & 1;
+        const u32 parity = ((j - j_begin) >> 1) & 1;
         const u32 jbase = ring_base + (j & 1) * (2 * KS_SLOT_BYTES) + col_off;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -487,8 +502,13 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
     for (int q = 0; q < KS_TILE; q++) {
         if (q < nct) {
             if (is_a) {
-                p.res_a[(ct0 + q) * KS_N + 2 * tid] = (i32)acc0[q];
-                p.res_a[(ct0 + q) * KS_N + 2 * tid + 1] = (i32)acc1[q];
+                if (!split) {
+                    p.res_a[(ct0 + q) * KS_N + 2 * tid] = (i32)acc0[q];
+                    p.res_a[(ct0 + q) * KS_N + 2 * tid + 1] = (i32)acc1[q];
+                } else {
+                    atomicAdd(reinterpret_cast<unsigned int *>(p.res_a + (ct0 + q) * KS_N + 2 * tid), acc0[q]);
+                    atomicAdd(reinterpret_cast<unsigned int *>(p.res_a + (ct0 + q) * KS_N + 2 * tid + 1), acc1[q]);
+                }
             }
         }
     }
