@@ -298,6 +298,51 @@ NB_HD void phase_inv1(int task, i32 *acc_all, const u64 *w_all, const u64 *twd_i
     });
 }
 
+// ---- stand-alone transforms (nb_ntt_*): same passes, 4 polynomials per sweep of 256 threads ----------
+constexpr int NTT_SWEEP_POLYS = 4;
+constexpr int NTT_SWEEP_THREADS = 64 * NTT_SWEEP_POLYS;
+
+// stored position (row, stored column) of the transformed element with natural index k
+NB_HD int w_position_of_natural(int k)
+{
+    int k1 = k & 15, k2 = k >> 4;
+    int row = brev(k1, 4), u = brev(k2 & 3, 2), i = brev(k2 >> 2, 4);
+    return row * ROW_STRIDE + col_of(u, i);
+}
+
+// first pass with generic inputs: task = (poly p, j2); x = canonical field elements, natural order
+NB_HD void phase_fwd1_generic(int task, const u64 *x /* 16 values, x[j1] = in[64 j1 + j2] */, u64 *w_all, const u64 *twd)
+{
+    const int j2 = task & 63, p = task >> 6;
+    u64 v[16];
+    static_for<0, 16>([&](auto J) {
+        constexpr int j1 = decltype(J)::value;
+        v[j1] = ff_shl<6 * j1>(x[j1]);
+    });
+    dif_inlane<4, 12, 0>(v);
+    u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        w[r * ROW_STRIDE] = ff_mul(v[r], twd[r * 64 + j2]);
+    });
+}
+// last inverse pass with generic outputs: y[j1] = out[64 j1 + j2], almost-canonical ([0, p])
+NB_HD void phase_inv1_generic(int task, u64 *y, const u64 *w_all, const u64 *twd_inv)
+{
+    const int j2 = task & 63, p = task >> 6;
+    const u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
+    u64 v[16];
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        v[r] = ff_mul(w[r * ROW_STRIDE], twd_inv[r * 64 + j2]);
+    });
+    dit_inlane<4, 12, 0>(v);
+    static_for<0, 16>([&](auto J) {
+        constexpr int j1 = decltype(J)::value;
+        y[j1] = ff_shl<(192 - 6 * j1) % 192>(v[j1]);
+    });
+}
+
 // thread -> task maps (tid in [0, 512), it = iteration)
 NB_HD void map_fwd2(int tid, int it, int &p, int &row, int &g)
 {

@@ -12,8 +12,7 @@ using namespace nb;
 struct nb_ctx {
     int device;
     cudaStream_t stream;
-    u64 *d_twd_fwd, *d_twd_inv;          // warp-NTT tables (stand-alone transforms)
-    u64 *d_ph_fwd, *d_ph_inv;            // phase tables (fused bootstrap)
+    u64 *d_ph_fwd, *d_ph_inv;            // middle-twiddle tables [row][j2] of the transform passes
     u64 *d_ones512;                      // 512 * NTT(all-ones), natural order (bk_prepare)
     int sm_count;
     int stagger_cycles;
@@ -49,7 +48,7 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     nb_ctx *ctx = new nb_ctx();
     ctx->device = device;
     ctx->stream = (cudaStream_t)stream;
-    ctx->d_twd_fwd = ctx->d_twd_inv = ctx->d_ph_fwd = ctx->d_ph_inv = ctx->d_ones512 = nullptr;
+    ctx->d_ph_fwd = ctx->d_ph_inv = ctx->d_ones512 = nullptr;
     *out = ctx;   // returned even on failure so that nb_last_error() can be read; caller destroys it
     NB_TRY(check(ctx, cudaSetDevice(device), "cudaSetDevice"));
     cudaDeviceProp prop;
@@ -62,11 +61,6 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     if (prop.major < 10)
         return fail(ctx, NB_EUNSUPPORTED, "libnufhe_b200 is built for sm_100a only; device is sm_" +
                                               std::to_string(prop.major) + std::to_string(prop.minor));
-    NttTables t;
-    NB_TRY(check(ctx, cudaMalloc(&ctx->d_twd_fwd, NTT_N * sizeof(u64)), "cudaMalloc"));
-    NB_TRY(check(ctx, cudaMalloc(&ctx->d_twd_inv, NTT_N * sizeof(u64)), "cudaMalloc"));
-    NB_TRY(check(ctx, cudaMemcpy(ctx->d_twd_fwd, t.fwd.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
-    NB_TRY(check(ctx, cudaMemcpy(ctx->d_twd_inv, t.inv.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
     PhaseTables pt;
     NB_TRY(check(ctx, cudaMalloc(&ctx->d_ph_fwd, NTT_N * sizeof(u64)), "cudaMalloc"));
     NB_TRY(check(ctx, cudaMalloc(&ctx->d_ph_inv, NTT_N * sizeof(u64)), "cudaMalloc"));
@@ -76,6 +70,10 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     NB_TRY(check(ctx, cudaMemcpy(ctx->d_ones512, pt.ones512.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)BR2_SMEM_BYTES), "cudaFuncSetAttribute(blind_rotate)"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_inverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
     return NB_OK;
 }
 
@@ -83,8 +81,6 @@ void nb_ctx_destroy(nb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->d_twd_fwd) cudaFree(ctx->d_twd_fwd);
-    if (ctx->d_twd_inv) cudaFree(ctx->d_twd_inv);
     if (ctx->d_ph_fwd) cudaFree(ctx->d_ph_fwd);
     if (ctx->d_ph_inv) cudaFree(ctx->d_ph_inv);
     if (ctx->d_ones512) cudaFree(ctx->d_ones512);
@@ -127,8 +123,8 @@ const char *nb_build_info(void)
 
 static int ntt_grid(nb_ctx *ctx, size_t batch)
 {
-    size_t blocks = (batch + 3) / 4;
-    size_t cap = (size_t)ctx->sm_count * 8;
+    size_t blocks = (batch + NTT_SWEEP_POLYS - 1) / NTT_SWEEP_POLYS;
+    size_t cap = (size_t)ctx->sm_count * 2;       // persistent: 2 CTAs per SM, grid-stride over the batch
     return (int)(blocks < cap ? blocks : cap);
 }
 
@@ -138,7 +134,7 @@ int nb_ntt_forward_i32(nb_ctx *ctx, const int32_t *in, uint64_t *out, size_t bat
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_i32: null argument");
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
-    ntt_forward_kernel<true><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>(in, (u64 *)out, ctx->d_twd_fwd, batch);
+    ntt_forward_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<i32>");
 }
 
@@ -148,7 +144,7 @@ int nb_ntt_forward_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_u64: null argument");
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
-    ntt_forward_kernel<false><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>(in, (u64 *)out, ctx->d_twd_fwd, batch);
+    ntt_forward_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<u64>");
 }
 
@@ -158,7 +154,7 @@ int nb_ntt_inverse_i32(nb_ctx *ctx, const uint64_t *in, int32_t *out, size_t bat
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_i32: null argument");
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
-    ntt_inverse_kernel<true><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>((const u64 *)in, out, ctx->d_twd_inv, batch);
+    ntt_inverse_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<i32>");
 }
 
@@ -168,7 +164,7 @@ int nb_ntt_inverse_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_u64: null argument");
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
-    ntt_inverse_kernel<false><<<ntt_grid(ctx, batch), 128, 0, ctx->stream>>>((const u64 *)in, out, ctx->d_twd_inv, batch);
+    ntt_inverse_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<u64>");
 }
 

@@ -1,7 +1,7 @@
-// host_emul.cpp -- runs the per-lane device code of ntt_lane.cuh on the CPU, one "warp" at a time
-// (32 lanes executed in sequence, the smem transpose replaced by an array transpose).  Built with g++
-// into libnb_host_emul.so for tests/test_lane_emulation.py: it lets the CPU-only test suite check the
-// index maps, twiddle tables and shift constants of the GPU transform against the oracle.
+// host_emul.cpp -- runs the __host__ __device__ pass code of br_phases.cuh / ntt_lane.cuh on the CPU, one
+// "thread" after the other, a phase at a time (a phase boundary = a CTA barrier).  Built with g++ into
+// libnb_host_emul.so for tests/test_host_logic.py: it lets the CPU-only test suite check the index maps,
+// swizzles, twiddle tables and shift constants of the GPU kernels against the oracle.
 // This is a test aid for the CUDA source, not a CPU fallback: nothing in nufhe_b200/ loads it.
 #include <cstring>
 #include <vector>
@@ -9,47 +9,37 @@
 
 using namespace nb;
 
-static const NttTables &tables() { static NttTables t; return t; }
-
-static void transpose(u64 v[32][32])
-{
-    for (int a = 0; a < 32; a++)
-        for (int b = a + 1; b < 32; b++) { u64 t = v[a][b]; v[a][b] = v[b][a]; v[b][a] = t; }
-}
-
 extern "C" {
 
-// in/out natural order, canonical
+// The stand-alone transform kernels' passes, one polynomial at a time; in/out natural order, canonical.
 void emul_ntt_forward(const u64 *in, u64 *out, size_t batch)
 {
-    const NttTables &T = tables();
+    static PhaseTables T;
+    std::vector<u64> w(NTT_SWEEP_POLYS * POLY_STRIDE);
     for (size_t b = 0; b < batch; b++) {
-        u64 v[32][32];
-        for (int l = 0; l < 32; l++) {
-            for (int s = 0; s < 32; s++) v[l][s] = ff_canon(in[b * NTT_N + ntt_in_index(l, s)]);
-            ntt_fwd_pre(v[l], T.fwd.data() + l, l);
+        for (int task = 0; task < 64; task++) {
+            u64 x[16];
+            for (int j1 = 0; j1 < 16; j1++) x[j1] = ff_canon(in[b * NTT_N + 64 * j1 + task]);
+            phase_fwd1_generic(task, x, w.data(), T.fwd.data());
         }
-        transpose(v);
-        for (int l = 0; l < 32; l++) {
-            ntt_fwd_post(v[l]);
-            for (int s = 0; s < 32; s++) out[b * NTT_N + ntt_out_index(l, s)] = v[l][s];
-        }
+        for (int row = 0; row < 16; row++) for (int g = 0; g < 4; g++) phase_fwd2(0, row, g, w.data());
+        for (int row = 0; row < 16; row++) for (int u = 0; u < 4; u++) phase_fwd3(0, row, u, w.data());
+        for (int k = 0; k < NTT_N; k++) out[b * NTT_N + k] = ff_canon(w[w_position_of_natural(k)]);
     }
 }
 
 void emul_ntt_inverse(const u64 *in, u64 *out, size_t batch)
 {
-    const NttTables &T = tables();
+    static PhaseTables T;
+    std::vector<u64> w(NTT_SWEEP_POLYS * POLY_STRIDE);
     for (size_t b = 0; b < batch; b++) {
-        u64 v[32][32];
-        for (int l = 0; l < 32; l++) {
-            for (int s = 0; s < 32; s++) v[l][s] = ff_canon(in[b * NTT_N + ntt_out_index(l, s)]);
-            ntt_inv_pre(v[l]);
-        }
-        transpose(v);
-        for (int l = 0; l < 32; l++) {
-            ntt_inv_post(v[l], T.inv.data() + l, l);
-            for (int s = 0; s < 32; s++) out[b * NTT_N + ntt_in_index(l, s)] = v[l][s];
+        for (int k = 0; k < NTT_N; k++) w[w_position_of_natural(k)] = ff_canon(in[b * NTT_N + k]);
+        for (int row = 0; row < 16; row++) for (int u = 0; u < 4; u++) phase_inv3(0, row, u, w.data());
+        for (int row = 0; row < 16; row++) for (int g = 0; g < 4; g++) phase_inv2(0, row, g, w.data());
+        for (int task = 0; task < 64; task++) {
+            u64 y[16];
+            phase_inv1_generic(task, y, w.data(), T.inv.data());
+            for (int j1 = 0; j1 < 16; j1++) out[b * NTT_N + 64 * j1 + task] = ff_canon(y[j1]);
         }
     }
 }

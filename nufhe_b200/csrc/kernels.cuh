@@ -19,92 +19,93 @@
 namespace nb {
 
 constexpr int LWE_N_MAX = 1024;          // upper bound on the LWE dimension n handled by the gate kernels
-constexpr int TR_STRIDE = 33;            // padded row of the transpose scratch (u64 units)
-constexpr int TR_WORDS = 32 * TR_STRIDE; // u64 per warp scratch
-
-// ---- warp transpose through shared memory: (slot s, lane l) <-> (slot l, lane s) ----------------
-NB_D void warp_transpose(u64 *v, u64 *scratch, int lane)
-{
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int s = 0; s < 32; s++) scratch[s * TR_STRIDE + lane] = v[s];
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < 32; s++) v[s] = scratch[lane * TR_STRIDE + s];
-    __syncwarp();
-#endif
-}
-
-NB_D void warp_ntt_forward(u64 *v, u64 *scratch, const u64 *twd_fwd, int lane)
-{
-    ntt_fwd_pre(v, twd_fwd + lane, lane);
-    warp_transpose(v, scratch, lane);
-    ntt_fwd_post(v);
-}
-
-NB_D void warp_ntt_inverse(u64 *v, u64 *scratch, const u64 *twd_inv, int lane)
-{
-    ntt_inv_pre(v);
-    warp_transpose(v, scratch, lane);
-    ntt_inv_post(v, twd_inv + lane, lane);
-}
-
 // ---- stand-alone batched transforms (reference: transform/computation.mako `standalone_transform`) ---
-// natural order in and out, one warp per polynomial, grid-stride over the batch.
+// natural order in and out.  Same three passes as the fused bootstrap (br_phases.cuh), 4 polynomials per
+// sweep of 256 threads, 2 CTAs per SM; the natural-order side is read / written with coalesced 128-byte
+// warp accesses and the re-ordering happens in shared memory.
+constexpr size_t NTTK_SMEM_BYTES = (size_t)NTT_SWEEP_POLYS * POLY_STRIDE * sizeof(u64) + NTT_N * sizeof(u64);
+
 template <bool IN_I32>
-__global__ void __launch_bounds__(128) ntt_forward_kernel(const void *__restrict__ in, u64 *__restrict__ out,
-                                                            const u64 *__restrict__ twd_fwd, size_t batch)
+__global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_forward_kernel(const void *__restrict__ in, u64 *__restrict__ out,
+                                                                            const u64 *__restrict__ twd_g, size_t batch)
 {
-    __shared__ u64 scratch_all[4 * TR_WORDS];
-    __shared__ u64 twd[NTT_N];
-    for (int i = threadIdx.x; i < NTT_N; i += blockDim.x) twd[i] = twd_fwd[i];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *w = reinterpret_cast<u64 *>(smem_raw);
+    u64 *twd = w + NTT_SWEEP_POLYS * POLY_STRIDE;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NTT_N; i += NTT_SWEEP_THREADS) twd[i] = twd_g[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 *scratch = scratch_all + warp * TR_WORDS;
-    // every warp of the CTA runs the same number of iterations (NB_LOCKSTEP barriers inside)
-    for (size_t p0 = (size_t)blockIdx.x * 4; p0 < batch; p0 += (size_t)gridDim.x * 4) {
-        const size_t p = p0 + warp;
-        const bool live = p < batch;
-        u64 v[32];
+    for (size_t p0 = (size_t)blockIdx.x * NTT_SWEEP_POLYS; p0 < batch; p0 += (size_t)gridDim.x * NTT_SWEEP_POLYS) {
+        {   // pass 1: thread = (poly, j2), reads x[64 j1 + j2]
+            const int pl = tid >> 6, j2 = tid & 63;
+            const size_t p = min(p0 + pl, batch - 1);
+            u64 x[16];
 #pragma unroll
-        for (int s = 0; s < 32; s++) {
-            size_t idx = (live ? p : p0) * NTT_N + ntt_in_index(lane, s);
-            if (IN_I32) v[s] = ff_from_i32(((const i32 *)in)[idx]);
-            else v[s] = ff_canon(((const u64 *)in)[idx]);
+            for (int j1 = 0; j1 < 16; j1++) {
+                const size_t idx = p * NTT_N + 64 * j1 + j2;
+                x[j1] = IN_I32 ? ff_from_i32(((const i32 *)in)[idx]) : ff_canon(((const u64 *)in)[idx]);
+            }
+            phase_fwd1_generic(tid, x, w, twd);
         }
-        warp_ntt_forward(v, scratch, twd, lane);
-        if (live) {
+        __syncthreads();
+        { const int g = tid >> 6, x = tid & 63; phase_fwd2(x >> 4, x & 15, g, w); }
+        __syncthreads();
+        { const int u = tid & 3, r = (tid >> 2) & 15, p = tid >> 6; phase_fwd3(p, r, u, w); }
+        __syncthreads();
+        // natural-order store: thread handles k = tid + 256 e of each polynomial
 #pragma unroll
-            for (int s = 0; s < 32; s++) out[p * NTT_N + ntt_out_index(lane, s)] = ff_canon(v[s]);
+        for (int pl = 0; pl < NTT_SWEEP_POLYS; pl++) {
+            if (p0 + pl < batch) {
+#pragma unroll
+                for (int e = 0; e < NTT_N / NTT_SWEEP_THREADS; e++) {
+                    const int k = tid + NTT_SWEEP_THREADS * e;
+                    out[(p0 + pl) * NTT_N + k] = ff_canon(w[pl * POLY_STRIDE + w_position_of_natural(k)]);
+                }
+            }
         }
+        __syncthreads();
     }
 }
 
 template <bool OUT_I32>
-__global__ void __launch_bounds__(128) ntt_inverse_kernel(const u64 *__restrict__ in, void *__restrict__ out,
-                                                            const u64 *__restrict__ twd_inv, size_t batch)
+__global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_inverse_kernel(const u64 *__restrict__ in, void *__restrict__ out,
+                                                                            const u64 *__restrict__ twd_g, size_t batch)
 {
-    __shared__ u64 scratch_all[4 * TR_WORDS];
-    __shared__ u64 twd[NTT_N];
-    for (int i = threadIdx.x; i < NTT_N; i += blockDim.x) twd[i] = twd_inv[i];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *w = reinterpret_cast<u64 *>(smem_raw);
+    u64 *twd = w + NTT_SWEEP_POLYS * POLY_STRIDE;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NTT_N; i += NTT_SWEEP_THREADS) twd[i] = twd_g[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 *scratch = scratch_all + warp * TR_WORDS;
-    for (size_t p0 = (size_t)blockIdx.x * 4; p0 < batch; p0 += (size_t)gridDim.x * 4) {
-        const size_t p = p0 + warp;
-        const bool live = p < batch;
-        u64 v[32];
+    for (size_t p0 = (size_t)blockIdx.x * NTT_SWEEP_POLYS; p0 < batch; p0 += (size_t)gridDim.x * NTT_SWEEP_POLYS) {
 #pragma unroll
-        for (int s = 0; s < 32; s++) v[s] = ff_canon(in[(live ? p : p0) * NTT_N + ntt_out_index(lane, s)]);
-        warp_ntt_inverse(v, scratch, twd, lane);
-        if (live) {
+        for (int pl = 0; pl < NTT_SWEEP_POLYS; pl++) {
+            const size_t p = min(p0 + pl, batch - 1);
 #pragma unroll
-            for (int s = 0; s < 32; s++) {
-                size_t idx = p * NTT_N + ntt_in_index(lane, s);
-                if (OUT_I32) ((i32 *)out)[idx] = ff_to_i32(v[s]);
-                else ((u64 *)out)[idx] = ff_canon(v[s]);
+            for (int e = 0; e < NTT_N / NTT_SWEEP_THREADS; e++) {
+                const int k = tid + NTT_SWEEP_THREADS * e;
+                w[pl * POLY_STRIDE + w_position_of_natural(k)] = ff_canon(in[p * NTT_N + k]);
             }
         }
+        __syncthreads();
+        { const int u = tid & 3, r = (tid >> 2) & 15, p = tid >> 6; phase_inv3(p, r, u, w); }
+        __syncthreads();
+        { const int g = tid >> 6, x = tid & 63; phase_inv2(x >> 4, x & 15, g, w); }
+        __syncthreads();
+        {
+            const int pl = tid >> 6, j2 = tid & 63;
+            u64 y[16];
+            phase_inv1_generic(tid, y, w, twd);
+            if (p0 + pl < batch) {
+#pragma unroll
+                for (int j1 = 0; j1 < 16; j1++) {
+                    const size_t idx = (p0 + pl) * NTT_N + 64 * j1 + j2;
+                    if (OUT_I32) ((i32 *)out)[idx] = ff_to_i32(ff_canon(y[j1]));
+                    else ((u64 *)out)[idx] = ff_canon(y[j1]);
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -1,7 +1,6 @@
 // tables.h -- host-side construction of the constant tables the kernels consume:
-//   * stage-T twiddles of the warp NTT (ntt_lane.cuh), forward and inverse, [slot][lane] order;
-//   * the permutation that takes a reference-format bootstrap-key row (natural NTT order,
-//     Montgomery form, nufhe/tlwe_gpu.py:199-236) to the lane-major plain form the MAC reads.
+//   * the middle twiddles psi^(j2 (2 k1 + 1)) of the transform passes (br_phases.cuh), forward and inverse;
+//   * 512 * NTT(all-ones), used for the correction planes of the engine-format bootstrap key.
 // Host only (uses unsigned __int128); shared by the CUDA library and the host lane emulator.
 #pragma once
 #include <vector>
@@ -15,21 +14,6 @@ inline u64 h_pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = h_mul(r, 
 inline u64 h_inv(u64 a) { return h_pow(a, FF_P - 2); }
 
 constexpr u64 ROOT_GEN = 0xa70dc47e4cbdf43fULL;          // nufhe/transform/ntt_cpu.py:109
-
-struct NttTables {
-    std::vector<u64> fwd, inv;     // [slot * 32 + lane]
-    NttTables() : fwd(NTT_N), inv(NTT_N)
-    {
-        const u64 psi = h_pow(ROOT_GEN, (1ULL << 32) / 2048);
-        const u64 psi_inv = h_inv(psi), n_inv = h_inv(NTT_N);
-        for (int slot = 0; slot < SLOTS; slot++)
-            for (int lane = 0; lane < 32; lane++) {
-                int e = ntt_twiddle_exponent(lane, slot);
-                fwd[slot * 32 + lane] = h_pow(psi, e);
-                inv[slot * 32 + lane] = h_mul(h_pow(psi_inv, e), n_inv);
-            }
-    }
-};
 
 // Tables of the phase-structured bootstrap kernel (br_phases.cuh): [row][j2], 64 entries per row.
 struct PhaseTables {
@@ -55,12 +39,5 @@ struct PhaseTables {
             }
     }
 };
-
-// Index into a reference BK row (2,2,2,1024) = [mi][j][mo][k] for element [mi][slot][j][lane][mo]
-// of the internal row layout (see kernels.cu: bk_prepare_kernel).
-inline size_t bk_internal_index(int mi, int slot, int j, int lane, int mo)
-{
-    return ((((size_t)mi * SLOTS + slot) * 2 + j) * 32 + lane) * 2 + mo;
-}
 
 }  // namespace nb
