@@ -71,6 +71,20 @@ def measured_peak_hbm():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic(batch):
+    """dram__bytes_read + dram__bytes_write of one blind-rotate launch from the committed ncu capture
+    (profiles/r1_traffic.json), only if it was taken at this batch size."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+            d = json.load(f)
+        if int(d['batch']) != int(batch):
+            return None
+        k = d['blind_rotate_kernel']
+        return int(k['dram_bytes_read']) + int(k['dram_bytes_write'])
+    except Exception:
+        return None
+
+
 def metric_name(args):
     return 'bootstrapped gates/sec (%s) at batch %d per GPU' % (args.gate.upper(), args.batch)
 
@@ -326,7 +340,8 @@ def run_b200_arm(args):
             'gpu_launches': launches_per_gate * args.steps,
             'clocks': sampler.summary(),
             'roofline': {'bound': 'hbm', 'kernel': 'blind_rotate_kernel', 'achieved': achieved, 'peak': peak,
-                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': measured_traffic(B),
+                         'algorithmic_bytes': alg_bytes,
                          'peak_source': peak_src, 'bytes_model': 'per-step: n*(16384*B+65536) per launch',
                          'ms_per_launch': br_avg_ms, 'share_of_step': br_avg_ms / ms_per_step,
                          'note': 'integer-issue bound, not HBM bound (SURVEY.md 8d); see profiles/'},
