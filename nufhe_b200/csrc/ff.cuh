@@ -108,47 +108,63 @@ NB_HD u64 ff_reduce128(u64 lo, u64 hi)
 }
 
 #if defined(__CUDA_ARCH__)
-// 64 x 64 -> 128 bit product as four 32-bit limbs: 4 IMAD.WIDE + 6 carry-chain adds
-NB_D void mul128(u64 a, u64 b, u32 &l, u32 &m, u32 &h0, u32 &h1)
+// 64 x 64 -> 128 bit product as four 32-bit limbs.  Written as mad.lo.cc / madc.hi.cc chains: ptxas turns
+// them into IMAD.WIDE / IMAD.HI with carry predicates, i.e. the carries ride on the FMA pipe and the ALU
+// pipe (the binding one, profiles/r1_final_summary.txt) sees a single SEL.
+NB_D void mul128(u64 a, u64 b, u32 &r0, u32 &r1, u32 &r2, u32 &r3)
 {
-    u64 p00, p01, p10, p11;
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p00) : "r"(lo32(a)), "r"(lo32(b)));
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p01) : "r"(lo32(a)), "r"(hi32(b)));
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p10) : "r"(hi32(a)), "r"(lo32(b)));
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p11) : "r"(hi32(a)), "r"(hi32(b)));
-    l = lo32(p00);
-    asm("add.cc.u32 %0, %3, %4;\n\t"
-        "addc.cc.u32 %1, %5, %6;\n\t"
-        "addc.u32 %2, %7, 0;\n\t"
-        "add.cc.u32 %0, %0, %8;\n\t"
-        "addc.cc.u32 %1, %1, %9;\n\t"
-        "addc.u32 %2, %2, 0;"
-        : "=&r"(m), "=&r"(h0), "=&r"(h1)
-        : "r"(hi32(p00)), "r"(lo32(p01)), "r"(hi32(p01)), "r"(lo32(p11)), "r"(hi32(p11)), "r"(lo32(p10)),
-          "r"(hi32(p10)));
+    asm("mul.lo.u32 %0, %4, %6;\n\t"
+        "mul.hi.u32 %1, %4, %6;\n\t"
+        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
+        "madc.hi.u32 %2, %4, %7, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+        "addc.u32 %3, 0, 0;\n\t"
+        "mad.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.u32 %3, %5, %7, %3;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
 }
-// l + m phi + h0 phi^2 + h1 phi^3 -> canonical: (m:l) - h1 (borrow fixed), + h0 * eps (carry fixed), canon
+// acc (5 limbs, acc4 small) += a * b
+NB_D void mac128(u64 a, u64 b, u32 &c0, u32 &c1, u32 &c2, u32 &c3, u32 &c4)
+{
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %8, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %8, %2;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.hi.cc.u32 %2, %6, %7, %2;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %8, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+}
+// l + m phi + h0 phi^2 + h1 phi^3 -> canonical: (m:l) - h1 (borrow fixed), + h0 * eps as a mad chain (carry
+// fixed), canon
 NB_D u64 ff_reduce_limbs(u32 l, u32 m, u32 h0, u32 h1)
 {
-    u32 u0, u1, r0, r1, k;
-    {
-        u64 t;
-        asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(h0), "r"(nb_c_eps));
-        u0 = lo32(t); u1 = hi32(t);
-    }
+    u32 r0, r1, k;
     asm("sub.cc.u32 %0, %3, %5;\n\t"
         "subc.cc.u32 %1, %4, 0;\n\t"
         "subc.u32 %2, 0, 0;\n\t"
         "sub.cc.u32 %0, %0, %2;\n\t"
         "subc.u32 %1, %1, 0;\n\t"
-        "add.cc.u32 %0, %0, %6;\n\t"
-        "addc.cc.u32 %1, %1, %7;\n\t"
-        "addc.u32 %2, 0, 0;\n\t"            // carry as 0/1 (an add-chain flag must be read by addc: ptxas keeps
-        "sub.cc.u32 %0, %0, %2;\n\t"        // subtraction borrows in the inverted sense, so never mix the two)
-        "subc.u32 %1, %1, 0;\n\t"           // + carry * eps = - carry + carry * 2^32
+        "mad.lo.cc.u32 %0, %6, 0xffffffff, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, 0xffffffff, %1;\n\t"
+        "addc.u32 %2, 0, 0;\n\t"              // carry as 0/1 (an add-chain flag must be read by addc: ptxas keeps
+        "sub.cc.u32 %0, %0, %2;\n\t"          // subtraction borrows in the inverted sense, so never mix the two)
+        "subc.u32 %1, %1, 0;\n\t"             // + carry * eps = - carry + carry * 2^32
         "add.u32 %1, %1, %2;"
         : "=&r"(r0), "=&r"(r1), "=&r"(k)
-        : "r"(l), "r"(m), "r"(h1), "r"(u0), "r"(u1));
+        : "r"(l), "r"(m), "r"(h1), "r"(h0));
     const bool ge = r1 == 0xffffffffu && r0 != 0u;
     return ge ? (u64)(r0 - 1u) : pack(r0, r1);
 }
@@ -177,14 +193,11 @@ NB_HD u64 ff_mul2_add(u64 a, u64 b, u64 c, u64 d)
 NB_HD u64 ff_dot4(const u64 *a, const u64 *b)
 {
 #if defined(__CUDA_ARCH__)
-    u64 lo = a[0] * b[0], hi = __umul64hi(a[0], b[0]);
-    u32 c = 0;
+    u32 c0, c1, c2, c3, c4 = 0;
+    mul128(a[0], b[0], c0, c1, c2, c3);
 #pragma unroll
-    for (int k = 1; k < 4; k++) {
-        u64 pl = a[k] * b[k], ph = __umul64hi(a[k], b[k]);
-        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
-            : "+l"(lo), "+l"(hi), "+r"(c) : "l"(pl), "l"(ph));
-    }
+    for (int k = 1; k < 4; k++) mac128(a[k], b[k], c0, c1, c2, c3, c4);
+    return ff_sub(ff_reduce_limbs(c0, c1, c2, c3), (u64)c4 << 32);
 #else
     unsigned __int128 acc = 0;
     u32 c = 0;
@@ -195,8 +208,8 @@ NB_HD u64 ff_dot4(const u64 *a, const u64 *b)
         acc = nx;
     }
     u64 lo = (u64)acc, hi = (u64)(acc >> 64);
-#endif
     return ff_sub(ff_reduce128(lo, hi), (u64)c << 32);
+#endif
 }
 
 // u * 2^(6*J1) for a small unsigned u < 2^10 (gadget digit + 512): the twist of the inner 16-point
@@ -298,25 +311,33 @@ NB_D u64 ff_add_loose_small(u32 w0, u32 w1, u32 u0, u32 u1)
         : "r"(w0), "r"(w1), "r"(u0), "r"(u1));
     return k ? pack(t0, t1) : pack(r0, r1);
 }
-// pattern a: (y0 - y2) + (y1 + y2) phi = pack(y0, y1) + y2 * eps
+// pattern a: (y0 - y2) + (y1 + y2) phi = pack(y0, y1) + y2 * eps.  The product and the 64-bit accumulate are one
+// mad.lo.cc / madc.hi.cc chain (carry on the FMA pipe); y2 * eps < 2^63, so one conditional subtraction of p.
 NB_D u64 ff_comb_a(u32 y0, u32 y1, u32 y2)
 {
-    u32 u0, u1;
-    mulwide(y2, nb_c_eps, u0, u1);
-    return ff_add_loose_small(y0, y1, u0, u1);
+    u32 r0, r1, t0, t1, k;
+    asm("mad.lo.cc.u32 %0, %7, 0xffffffff, %5;\n\t"
+        "madc.hi.cc.u32 %1, %7, 0xffffffff, %6;\n\t"
+        "addc.u32 %4, 0, 0;\n\t"
+        "add.cc.u32 %2, %0, 0xffffffff;\n\t"
+        "addc.cc.u32 %3, %1, 0;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(t0), "=&r"(t1), "=&r"(k)
+        : "r"(y0), "r"(y1), "r"(y2));
+    return k ? pack(t0, t1) : pack(r0, r1);
 }
 // pattern b: (-y1 - y2) + (y0 + y1) phi = y0 * 2^32 + y1 * eps - y2
 NB_D u64 ff_comb_b(u32 y0, u32 y1, u32 y2)
 {
-    u32 u0, u1, lo, hi, k, ks;
-    mulwide(y1, nb_c_eps, u0, u1);
-    asm("add.cc.u32 %1, %4, %5;\n\t"        // hi = u1 + y0
-        "addc.u32 %2, 0, 0;\n\t"            // k = carry
-        "sub.cc.u32 %0, %3, %6;\n\t"        // lo = u0 - y2
+    u32 lo, hi, k, ks;
+    asm("mad.lo.cc.u32 %0, %4, 0xffffffff, 0;\n\t"     // lo = low(y1 * eps)
+        "madc.hi.cc.u32 %1, %4, 0xffffffff, %3;\n\t"   // hi = high(y1 * eps) + y0
+        "addc.u32 %2, 0, 0;\n\t"                       // k = carry
+        "sub.cc.u32 %0, %0, %5;\n\t"                   // - y2
         "subc.cc.u32 %1, %1, 0;\n\t"
-        "subc.u32 %2, %2, 0;"                 // k in {-1, 0, 1}; -1 only when y0 = y1 = 0 < y2
+        "subc.u32 %2, %2, 0;"                            // k in {-1, 0, 1}; -1 only when y0 = y1 = 0 < y2
         : "=&r"(lo), "=&r"(hi), "=&r"(k)
-        : "r"(u0), "r"(u1), "r"(y0), "r"(y2));
+        : "r"(y0), "r"(y1), "r"(y2));
     // fold k * 2^64 = k * eps: (hi:lo) - k + k * 2^32 (two's complement k)
     ks = (u32)((i32)k >> 31);
     asm("sub.cc.u32 %0, %0, %2;\n\t"
