@@ -234,7 +234,7 @@ def run_b200_arm(args):
     dest = vm.empty_ciphertext((B,))
     gate = getattr(vm, 'gate_' + args.gate)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=thr.device)   # > 126 MB L2
-    launches_per_gate = 2 if args.gate == 'nand' else 3
+    launches_per_gate = 2          # fused bootstrap(s) + key switch, for NAND and for MUX alike
 
     def barrier():
         if world > 1:

@@ -83,6 +83,14 @@ int nb_bootstrap_extract(nb_ctx *ctx, const int32_t *in1_a, const int32_t *in1_b
                          const int32_t *in2_b, int32_t c, int32_t s1, int32_t s2, int32_t mu,
                          const uint64_t *bk_int, size_t n, int32_t *out_a, int32_t *out_b, size_t batch);
 
+/* Two bootstraps in one launch (gate_mux, gates.py:638-655): job A on ciphertexts [0, B), job B on [B, 2B);
+ * out_a (2B,1024), out_b (2B,).  Halves the latency of small-batch MUX gates. */
+int nb_bootstrap_extract2(nb_ctx *ctx, const int32_t *a1_a, const int32_t *a1_b, const int32_t *a2_a,
+                          const int32_t *a2_b, int32_t a_c, int32_t a_s1, int32_t a_s2, const int32_t *b1_a,
+                          const int32_t *b1_b, const int32_t *b2_a, const int32_t *b2_b, int32_t b_c, int32_t b_s1,
+                          int32_t b_s2, int32_t mu, const uint64_t *bk_int, size_t n, int32_t *out_a, int32_t *out_b,
+                          size_t batch);
+
 /* ---- lwe_keyswitch (lwe.py:311-322): res = keyswitch((0, c) + src1 + src2), src2 may be NULL.
  * res_cv may be NULL. */
 int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, const int32_t *src2_a,

@@ -177,6 +177,11 @@ struct BlindRotateArgs {
     //                bootstrap(mu, x) (bootstrap.py:206-229).  in2 may be null (s2 ignored).
     const i32 *in1_a, *in1_b, *in2_a, *in2_b;
     i32 c, s1, s2, mu;
+    // optional second job over the same launch (gate_mux's two bootstraps, gates.py:638-655): ciphertexts
+    // [job_batch, 2 job_batch) use these operands / signs instead; outputs are simply the next rows
+    const i32 *j2_in1_a, *j2_in1_b, *j2_in2_a, *j2_in2_b;
+    i32 j2_c, j2_s1, j2_s2;
+    size_t job_batch;       // 0: single job
     // mode B (BlindRotate_gpu, blind_rotate.py:262-281): explicit accumulator (B,2,1024) and bara (B,n)
     const i32 *accum, *bara;
     const u64 *bk;          // internal layout, n rows
@@ -213,6 +218,11 @@ NB_D Br2Smem br2_carve(unsigned char *raw)
 NB_D int br2_rotation(const BlindRotateArgs &p, size_t c, int i)
 {
     if (p.bara) return p.bara[c * p.n + i];
+    if (p.job_batch && c >= p.job_batch) {
+        const size_t d = c - p.job_batch;
+        i32 xa = p.j2_s1 * p.j2_in1_a[d * p.n + i] + (p.j2_in2_a ? p.j2_s2 * p.j2_in2_a[d * p.n + i] : 0);
+        return modswitch_2n(xa);
+    }
     i32 xa = p.s1 * p.in1_a[c * p.n + i] + (p.in2_a ? p.s2 * p.in2_a[c * p.n + i] : 0);
     return modswitch_2n(xa);
 }
@@ -273,7 +283,13 @@ __global__ void __launch_bounds__(BR2_THREADS, BR2_CTAS_PER_SM) blind_rotate_ker
             val = p.accum[(c * 2 + mi) * NTT_N + x];
         } else {
             // ACC = (0, X^(2N - barb) * [mu, ..., mu])   (bootstrap.py:177-182, 224)
-            i32 xb = p.c + p.s1 * p.in1_b[c] + (p.in2_b ? p.s2 * p.in2_b[c] : 0);
+            i32 xb;
+            if (p.job_batch && c >= p.job_batch) {
+                const size_t d = c - p.job_batch;
+                xb = p.j2_c + p.j2_s1 * p.j2_in1_b[d] + (p.j2_in2_b ? p.j2_s2 * p.j2_in2_b[d] : 0);
+            } else {
+                xb = p.c + p.s1 * p.in1_b[c] + (p.in2_b ? p.s2 * p.in2_b[c] : 0);
+            }
             int q = 2 * NTT_N - modswitch_2n(xb);
             if (q < NTT_N) val = x < q ? (i32)(0u - (u32)p.mu) : p.mu;
             else val = x < q - NTT_N ? p.mu : (i32)(0u - (u32)p.mu);

@@ -153,6 +153,25 @@ class Engine:
                    int(mu), _ptr(bk_int), n, _ptr(out_a), _ptr(out_b), B)
         return out_a, out_b
 
+    def bootstrap_extract2(self, job_a, job_b, mu, bk_int):
+        """Two bootstraps in one launch.  job = (x1, x2, c, s1, s2) as for bootstrap_extract.
+        Returns two extracted samples (views of one (2B, 1024) / (2B,) allocation)."""
+        def parts(job):
+            x1, x2, c, s1, s2 = job
+            a1, b1 = self._dense(x1[0], torch.int32), self._dense(x1[1], torch.int32)
+            a2 = b2 = None
+            if x2 is not None:
+                a2, b2 = self._dense(x2[0], torch.int32), self._dense(x2[1], torch.int32)
+            return a1, b1, a2, b2, int(c), int(s1), int(s2)
+        pa, pb = parts(job_a), parts(job_b)
+        B = pa[1].numel()
+        n = pa[0].numel() // B
+        out_a, out_b = self.empty((2 * B, N), torch.int32), self.empty((2 * B,), torch.int32)
+        self._call('nb_bootstrap_extract2', _ptr(pa[0]), _ptr(pa[1]), _ptr(pa[2]), _ptr(pa[3]), pa[4], pa[5], pa[6],
+                   _ptr(pb[0]), _ptr(pb[1]), _ptr(pb[2]), _ptr(pb[3]), pb[4], pb[5], pb[6], int(mu), _ptr(bk_int), n,
+                   _ptr(out_a), _ptr(out_b), B)
+        return (out_a[:B], out_b[:B]), (out_a[B:], out_b[B:])
+
     def keyswitch(self, ks, src1, src2=None, c=0, out=None, want_cv=False):
         ks_a, ks_b, ks_cv = ks
         in_size, t, base, n = ks_a.shape

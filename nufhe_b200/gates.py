@@ -9,6 +9,7 @@ from .numeric_functions import phase_to_t32
 from .lwe import (
     LweSampleArray, lwe_negate, lwe_copy, lwe_noiseless_trivial, _keyswitch_into)
 from .bootstrap import bootstrap_affine
+from .tgsw import engine_format
 from .performance import PerformanceParameters, PerformanceParametersForDevice
 
 
@@ -137,10 +138,25 @@ def gate_mux(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, b: LweSa
     sum folded into the key-switch kernel's load."""
     check_shape(result, a, b, c)
     bk, ks = cloud_key.bootstrap_key, cloud_key.keyswitch_key
-    extracted_params = cloud_key.params.tgsw_params.tlwe_params.extracted_lweparams
-    u1 = LweSampleArray.empty(thr, extracted_params, result.shape)
-    u2 = LweSampleArray.empty(thr, extracted_params, result.shape)
     and_const = phase_to_t32(-1, 8)
-    bootstrap_affine(thr, u1, bk, ks, MU, a, b, and_const, 1, 1, no_keyswitch=True)     # AND(a, b)
-    bootstrap_affine(thr, u2, bk, ks, MU, a, c, and_const, -1, 1, no_keyswitch=True)    # AND(not a, c)
-    _keyswitch_into(thr, result, ks, u1, u2, phase_to_t32(1, 8))
+    shape = tuple(result.shape)
+
+    def expand(x):
+        a, b = x.a, x.b
+        if tuple(b.shape) != shape:
+            while b.dim() < len(shape):
+                a, b = a.unsqueeze(0), b.unsqueeze(0)
+            a, b = a.expand(shape + (a.shape[-1],)), b.expand(shape)
+        return (a.contiguous(), b.contiguous())
+
+    pa, pb, pc = expand(a), expand(b), expand(c)
+    # AND(a, b) and AND(not a, c) as two jobs of ONE launch, then one key switch of (0,1/8) + u1 + u2
+    u1, u2 = thr.bootstrap_extract2((pa, pb, and_const, 1, 1), (pa, pc, and_const, -1, 1), MU,
+                                    engine_format(thr, bk.tgsw))
+    dense = result.a.is_contiguous() and result.b.is_contiguous()
+    res_a, res_b, res_cv = thr.keyswitch(ks.device_arrays(), u1, u2, c=phase_to_t32(1, 8),
+                                         out=(result.a, result.b) if dense else None, want_cv=True)
+    if not dense:
+        result.a.copy_(res_a.reshape(result.a.shape))
+        result.b.copy_(res_b.reshape(result.b.shape))
+    result.current_variances.copy_(res_cv.reshape(result.current_variances.shape))

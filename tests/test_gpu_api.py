@@ -94,6 +94,19 @@ def test_mux_not_copy_constant(ctx, key_pair):
     assert (ctx.decrypt(sk, dest) == numpy.broadcast_to(c[1], (2, 8))).all()
 
 
+def test_mux_bit_exact_vs_oracle(ctx, key_pair, okeys):
+    """vm.gate_mux (two bootstraps in one launch + fused key switch) against the oracle's gate_mux."""
+    sk, ck = key_pair
+    vm = ctx.make_virtual_machine(ck)
+    rng = numpy.random.RandomState(6)
+    bits = [rng.randint(0, 2, 7).astype(bool) for _ in range(3)]
+    cts = [ctx.encrypt(sk, b) for b in bits]
+    r = vm.gate_mux(*cts)
+    want = O.gate_mux(*[(host(c.a), host(c.b)) for c in cts], okeys.bk, okeys.ks)
+    assert (host(r.a) == want[0]).all() and (host(r.b) == want[1]).all()
+    assert (ctx.decrypt(sk, r) == numpy.where(bits[0], bits[1], bits[2])).all()
+
+
 def test_broadcasting_views_and_dest(ctx, key_pair):
     sk, ck = key_pair
     vm = ctx.make_virtual_machine(ck)

@@ -77,6 +77,28 @@ struct V6 {
     }
 };
 
+// V7: add through IMAD.WIDE carry chains: s = a + b0 (wide mad, carry out), hi += b1 (carry out), then + eps with
+// carry out; select.  sub as in V1.
+struct V7 {
+    static __device__ __forceinline__ u64 sub(u64 a, u64 b) { return ff_sub(a, b); }
+    static __device__ __forceinline__ u64 add(u64 a, u64 b)
+    {
+        u32 s0, s1, t0, t1, k;
+        const u32 one = c_one;
+        asm("mad.lo.cc.u32 %0, %7, %9, %5;\n\t"       // s = a + b0 * one      (IMAD.WIDE with carry out)
+            "madc.hi.cc.u32 %1, %7, %9, %6;\n\t"
+            "addc.u32 %4, 0, 0;\n\t"
+            "add.cc.u32 %1, %1, %8;\n\t"              // hi += b1
+            "addc.u32 %4, %4, 0;\n\t"
+            "mad.lo.cc.u32 %2, %10, %9, %0;\n\t"      // t = s + eps * one
+            "madc.hi.cc.u32 %3, %10, %9, %1;\n\t"
+            "addc.u32 %4, %4, 0;"
+            : "=&r"(s0), "=&r"(s1), "=&r"(t0), "=&r"(t1), "=&r"(k)
+            : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)), "r"(one), "r"(c_eps32));
+        return k ? pack(t0, t1) : pack(s0, s1);
+    }
+};
+
 template <class V> __global__ void __launch_bounds__(512) kern(u64 *io, int iters, long long *cycles)
 {
     u64 v[16];
@@ -125,5 +147,6 @@ int main()
     run<V4>("V4 no reduction (lower bound)", io, dcyc);
     run<V5>("V5 add-chain fix (IMAD.X friendly)", io, dcyc);
     run<V6>("V6 V5 sub + add via carry select", io, dcyc);
+    run<V7>("V7 add via IMAD.WIDE carry chains", io, dcyc);
     return 0;
 }
