@@ -75,3 +75,43 @@ def test_mux_vs_oracle(eng, keys, dev_keys):
     want = O.gate_mux(a, b, c, keys.bk, keys.ks)
     assert (eng.to_host(ra) == want[0]).all() and (eng.to_host(rb) == want[1]).all()
     assert (keys.decrypt((eng.to_host(ra), eng.to_host(rb))) == numpy.where(bits[0], bits[1], bits[2])).all()
+
+
+def test_nand_more_than_one_wave_vs_oracle(eng, keys, dev_keys):
+    """600 ciphertexts = 300 CTAs > the 296 co-resident ones: exercises CTA turnover; every (a, b) is compared."""
+    rng = G.rs(470)
+    B = 600
+    bits_a, bits_b = rng.randint(0, 2, B).astype(bool), rng.randint(0, 2, B).astype(bool)
+    a, b = keys.encrypt(bits_a), keys.encrypt(bits_b)
+    ext, out = gpu_gate(eng, dev_keys, 'nand', a, b)
+    want = O.gate_binary('nand', a, b, keys.bk, keys.ks)
+    assert (out[0] == want[0]).all() and (out[1] == want[1]).all()
+    assert (keys.decrypt(out) == ~(bits_a & bits_b)).all()
+
+
+@pytest.mark.parametrize('batch', [4096, 16384])
+def test_full_size_batches_decrypt_to_truth_table(eng, keys, dev_keys, batch):
+    """BASELINE.json batch sizes: size-independent property (encrypt -> gate -> decrypt == truth table) for
+    NAND and MUX, plus determinism (two runs give identical ciphertexts) and batch-independence (the first
+    37 outputs equal those of a 37-ciphertext run)."""
+    bk_int, ks = dev_keys
+    rng = G.rs(480 + batch)
+    bits = [rng.randint(0, 2, batch).astype(bool) for _ in range(3)]
+    cts = [keys.encrypt(x) for x in bits]
+    d = [(eng.to_device(x[0]), eng.to_device(x[1])) for x in cts]
+    num, den, sa, sb = O.GATE_TABLE['nand']
+    ext = eng.bootstrap_extract(d[0], d[1], O.phase_to_t32(num, den), sa, sb, O.MU, bk_int)
+    ra, rb, _ = eng.keyswitch(ks, ext)
+    out = (eng.to_host(ra), eng.to_host(rb))
+    assert (keys.decrypt(out) == ~(bits[0] & bits[1])).all()
+    ext2 = eng.bootstrap_extract(d[0], d[1], O.phase_to_t32(num, den), sa, sb, O.MU, bk_int)
+    ra2, rb2, _ = eng.keyswitch(ks, ext2)
+    assert torch.equal(ra, ra2) and torch.equal(rb, rb2)
+    small = [(x[0][:37].contiguous(), x[1][:37].contiguous()) for x in d[:2]]
+    ext3 = eng.bootstrap_extract(small[0], small[1], O.phase_to_t32(num, den), sa, sb, O.MU, bk_int)
+    ra3, rb3, _ = eng.keyswitch(ks, ext3)
+    assert torch.equal(ra[:37], ra3) and torch.equal(rb[:37], rb3)
+    and_const = O.phase_to_t32(-1, 8)
+    u1, u2 = eng.bootstrap_extract2((d[0], d[1], and_const, 1, 1), (d[0], d[2], and_const, -1, 1), O.MU, bk_int)
+    ma, mb, _ = eng.keyswitch(ks, u1, u2, c=O.phase_to_t32(1, 8))
+    assert (keys.decrypt((eng.to_host(ma), eng.to_host(mb))) == numpy.where(bits[0], bits[1], bits[2])).all()
