@@ -260,7 +260,17 @@ def golden_gate():
          nand_bits=(dec > 0))
 
 
+def golden_params_pickle():
+    """The parameter object every nufhe dump starts with, pickled by the reference's own class."""
+    import pickle
+    path = os.path.join(HERE, 'ref_params.pkl')
+    with open(path, 'wb') as f:
+        pickle.dump(NuFHEParameters(), f)
+    print('wrote', path)
+
+
 if __name__ == '__main__':
+    golden_params_pickle()
     golden_arithmetic()
     golden_ntt()
     golden_small()

@@ -186,6 +186,21 @@ def test_low_level_api(key_pair, okeys, nufhe):
     assert (host(ext.a) == want[0]).all() and (host(ext.b) == want[1]).all()
 
 
+def test_uint_min_circuit(ctx, key_pair):
+    """operators_integer.uint_min (test_gates.py:248-249 of the reference): 8-bit encrypted minimum."""
+    from nufhe_b200.operators_integer import uint_min, uintarray_to_bitarray, bitarray_to_uintarray
+    sk, ck = key_pair
+    vm = ctx.make_virtual_machine(ck)
+    rng = numpy.random.RandomState(8)
+    xs, ys = rng.randint(0, 256, 6).astype(numpy.uint8), rng.randint(0, 256, 6).astype(numpy.uint8)
+    xs[0], ys[0] = 17, 17
+    ca, cb = ctx.encrypt(sk, uintarray_to_bitarray(xs)), ctx.encrypt(sk, uintarray_to_bitarray(ys))
+    answer = vm.empty_ciphertext((6, 8))
+    uint_min(ctx.thread, ck, answer, ca, cb, perf_params=vm.perf_params)
+    got = bitarray_to_uintarray(ctx.decrypt(sk, answer))
+    assert (got == numpy.minimum(xs, ys)).all()
+
+
 def test_find_devices(nufhe):
     devs = nufhe.find_devices()
     assert len(devs) >= 1 and devs[0].api_name == 'CUDA'

@@ -176,3 +176,43 @@ def test_phase_structured_step_matches_oracle(emul):
         a = acc.copy()
         emul.emul_phase_step(_p(a), _p(bk[0]), _p(rot), ctypes.c_int(nct))
         assert (a == O.blind_rotate(acc, bk[0:1], rot.reshape(nct, 1))).all()
+
+
+def test_uint_bit_helpers_roundtrip():
+    from nufhe_b200.operators_integer import uintarray_to_bitarray, bitarray_to_uintarray
+    xs = numpy.array([[0, 1, 255], [128, 77, 200]], numpy.uint8)
+    bits = uintarray_to_bitarray(xs)
+    assert bits.shape == (2, 3, 8) and bits[0, 1].tolist() == [False] * 7 + [True]
+    assert (bitarray_to_uintarray(bits) == xs).all()
+    ys = numpy.array([0, 1, 2**31, 2**32 - 1], numpy.uint32)
+    assert (bitarray_to_uintarray(uintarray_to_bitarray(ys)) == ys).all()
+
+
+def test_pickle_wire_compatibility_with_reference_parameter_classes():
+    """The parameter objects nufhe pickles into every dump: ours carry the same attributes and, with
+    compat.use_reference_pickle_paths(), the same class paths; a pickle made by the REFERENCE's classes
+    (committed as tests/golden/ref_params.pkl by make_golden.py) loads into ours and compares equal."""
+    import pickle
+    import subprocess
+    import sys
+    code = r'''
+import pickle, sys
+sys.path.insert(0, %r)
+import nufhe_b200
+from nufhe_b200 import compat
+compat.use_reference_pickle_paths()
+p = nufhe_b200.NuFHEParameters()
+blob = pickle.dumps(p)
+assert b'nufhe.api_low_level' in blob and b'nufhe_b200' not in blob, blob[:200]
+q = pickle.loads(blob)
+assert q == p and q.in_out_params == p.in_out_params and q.tgsw_params == p.tgsw_params
+ref = pickle.load(open(%r, 'rb'))
+assert type(ref).__name__ == 'NuFHEParameters' and type(ref).__module__ == 'nufhe.api_low_level'
+assert ref == p
+assert ref.in_out_params.size == 500 and ref.tgsw_params.tlwe_params.polynomial_degree == 1024
+assert int(ref.tgsw_params.offset) == int(p.tgsw_params.offset)
+assert (ref.tgsw_params.base_powers == p.tgsw_params.base_powers).all()
+print('ok')
+''' % (ROOT, os.path.join(ROOT, 'tests', 'golden', 'ref_params.pkl'))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr
