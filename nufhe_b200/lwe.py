@@ -104,14 +104,25 @@ class LweSampleArray:
     def shape(self):
         return self.shape_info.shape
 
+    def _a_index(self, index):
+        """The message-shape index applied to `a`, whose last axis is the LWE dimension: an Ellipsis must
+        not swallow that axis."""
+        idx = index if isinstance(index, tuple) else (index,)
+        if any(i is Ellipsis for i in idx):
+            pos = [k for k, i in enumerate(idx) if i is Ellipsis][0]
+            consumed = sum(1 for i in idx if i is not Ellipsis and i is not None)
+            fill = (slice(None),) * (len(self.shape) - consumed)
+            idx = idx[:pos] + fill + idx[pos + 1:]
+        return idx
+
     def __getitem__(self, index):
         return LweSampleArray(
-            self.params, self.a[index], self.b[index], self.current_variances[index])
+            self.params, self.a[self._a_index(index)], self.b[index], self.current_variances[index])
 
     def __setitem__(self, index, value):
         if not isinstance(value, LweSampleArray):
             raise ValueError("Only assignment of ciphertexts is supported")
-        self.a[index] = value.a
+        self.a[self._a_index(index)] = value.a
         self.b[index] = value.b
         self.current_variances[index] = value.current_variances
 
