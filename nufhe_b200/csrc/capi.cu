@@ -282,15 +282,14 @@ int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, cons
     if (t == 8 && log2_base == 2 && in_size == (size_t)KS_IN && n == (size_t)KS_N) {
         NB_TRY(check(ctx, cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)KS_SMEM_BYTES), "cudaFuncSetAttribute(keyswitch)"));
-        // one wave if possible: spread the batch over the SMs, at most KS_TILE ciphertexts per CTA
-        size_t tile = (batch + ctx->sm_count - 1) / ctx->sm_count;
-        if (tile > KS_TILE) tile = KS_TILE;
-        if (tile < 1) tile = 1;
+        // The consumer loop always walks KS_TILE ciphertext slots, so a CTA costs the same whatever its tile:
+        // fill the tiles, then split the 1024 input coefficients over blockIdx.y until the SMs are covered
+        // (partial sums meet in integer atomics).  One ciphertext: 128 CTAs x 8 coefficients.
+        size_t tile = batch < (size_t)KS_TILE ? batch : (size_t)KS_TILE;
         p.tile = (int)tile;
         int grid = (int)((batch + tile - 1) / tile);
-        // small batches: split the 1024 input coefficients over blockIdx.y and accumulate with atomics
         int splits = ctx->sm_count / grid;
-        if (splits > 32) splits = 32;
+        if (splits > 128) splits = 128;
         if (splits < 1) splits = 1;
         p.splits = splits;
         if (splits > 1) {

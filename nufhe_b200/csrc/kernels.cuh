@@ -410,8 +410,9 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
     }
     // packed digits of the tile: the 8 two-bit digits of coefficient j of ciphertext q in 16 bits
     const u32 prec_offset = 1u << (32 - (1 + 2 * 8));
-    for (int idx = tid; idx < KS_TILE * KS_IN; idx += KS_THREADS) {
-        const int q = idx / KS_IN, j = idx % KS_IN;
+    const int jn = max(j_end - j_begin, 0);
+    for (int idx = tid; idx < KS_TILE * jn; idx += KS_THREADS) {
+        const int q = idx / jn, j = j_begin + idx % jn;
         u32 v = 0;
         if (q < nct) {
             v = (u32)p.src1_a[(ct0 + q) * KS_IN + j];

@@ -153,7 +153,7 @@ def test_keyswitch_ragged_batches(eng):
     ks_a, ks_b, ks_cv, _, _ = G.keyswitch_inputs()
     ks = (eng.to_device(ks_a), eng.to_device(ks_b), eng.to_device(ks_cv))
     rng = G.rs(14)
-    for B in (1, 7, 8, 9, 33):
+    for B in (1, 7, 8, 9, 33, 160, 600):
         src_a, src_b = G.torus32(rng, (B, 1024)), G.torus32(rng, (B,))
         src2_a, src2_b = G.torus32(rng, (B, 1024)), G.torus32(rng, (B,))
         ra, rb, _ = eng.keyswitch(ks, (eng.to_device(src_a), eng.to_device(src_b)))
