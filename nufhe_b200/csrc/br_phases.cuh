@@ -293,8 +293,14 @@ NB_HD void phase_inv1(int task, i32 *acc_all, const u64 *w_all, const u64 *twd_i
     static_for<0, 16>([&](auto J) {
         constexpr int j1 = decltype(J)::value;
         const int idx = 64 * j1 + j2;
-        i32 r = ff_to_i32(ff_shl<(192 - 6 * j1) % 192>(v[j1]));
-        acc[idx] = ACCUMULATE ? (i32)((u32)acc[idx] + (u32)r) : r;
+        // 2^(-6 j1) = -2^(96 - 6 j1) for j1 >= 1: shift by the positive amount and subtract (the centred lift is odd)
+        if constexpr (j1 == 0) {
+            i32 r = ff_to_i32(v[0]);
+            acc[idx] = ACCUMULATE ? (i32)((u32)acc[idx] + (u32)r) : r;
+        } else {
+            u32 r = (u32)ff_to_i32(ff_shl<96 - 6 * j1>(v[j1]));
+            acc[idx] = ACCUMULATE ? (i32)((u32)acc[idx] - r) : (i32)(0u - r);
+        }
     });
 }
 

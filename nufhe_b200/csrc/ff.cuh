@@ -63,16 +63,19 @@ NB_HD u64 ff_canon(u64 x) { return x >= FF_P ? x - FF_P : x; }
 NB_HD u64 ff_sub(u64 a, u64 b)
 {
 #if defined(__CUDA_ARCH__)
+    // d = a - b mod 2^64 with borrow; the fix "- borrow * eps" runs on the FMA pipe: with m = -borrow (0 or
+    // 2^32 - 1), d + m * m = d + borrow * (1 - 2^33) is ONE IMAD.WIDE with a 64-bit addend (ptxas fuses the
+    // mad.lo.cc / madc.hi pair), and hi -= m adds borrow * 2^32.  Only the first two instructions are tied to
+    // the ALU pipe (the binding one, profiles/r1_final_summary.txt); the old 5-instruction borrow chain had four.
     u32 l, h, m;
     asm("sub.cc.u32 %0, %3, %5;\n\t"
         "subc.cc.u32 %1, %4, %6;\n\t"
         "subc.u32 %2, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, %2;\n\t"
-        "subc.u32 %1, %1, 0;"
+        "mad.lo.cc.u32 %0, %2, %2, %0;\n\t"
+        "madc.hi.u32 %1, %2, %2, %1;"
         : "=&r"(l), "=&r"(h), "=&r"(m)
         : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
-    (void)m;
-    return pack(l, h);
+    return pack(l, h - m);
 #else
     u64 d = a - b;
     return a < b ? d - FF_EPS : d;
@@ -147,26 +150,44 @@ NB_D void mac128(u64 a, u64 b, u32 &c0, u32 &c1, u32 &c2, u32 &c3, u32 &c4)
         : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
         : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
 }
-// l + m phi + h0 phi^2 + h1 phi^3 -> canonical: (m:l) - h1 (borrow fixed), + h0 * eps as a mad chain (carry
-// fixed), canon
+// v + k * eps for k in {0, 1}: one IMAD.WIDE (the multiplier comes from the constant bank so that ptxas keeps
+// the multiply); used for "subtract p when v >= p" (v + eps wraps to v - p) and for carry folds.
+NB_D u64 ff_add_keps(u32 v0, u32 v1, u32 k)
+{
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, %1;"
+        : "+r"(v0), "+r"(v1) : "r"(k), "r"(nb_c_eps));
+    return pack(v0, v1);
+}
+// any 64-bit v -> [0, p]: v - p if v > p (v = p is left alone: "almost canonical")
+NB_D u64 ff_canon_dev(u32 v0, u32 v1)
+{
+    u32 f;                                    // f = carry out of v + (2^32 - 2) = [v1 == 2^32 - 1 and v0 >= 2]
+    asm("add.cc.u32 %0, %1, 0xfffffffe;\n\t"
+        "addc.cc.u32 %0, %2, 0;\n\t"
+        "addc.u32 %0, 0, 0;"
+        : "=&r"(f) : "r"(v0), "r"(v1));
+    return ff_add_keps(v0, v1, f);
+}
+// l + m phi + h0 phi^2 + h1 phi^3 -> [0, p].  With phi^2 = phi - 1 and phi^3 = -1 the value is
+// l + (m + h0) phi - (h0 + h1); the carry c of mu = m + h0 is c phi^2 = c phi - c, and mu + c cannot overflow
+// (c = 1 implies mu <= 2^32 - 2), so it is the 64-bit difference  ((mu + c) : l) - (h0 + h1 + c)  >= -2^33 - 1,
+// one borrow fix (as in ff_sub) and one conditional subtraction of p.
 NB_D u64 ff_reduce_limbs(u32 l, u32 m, u32 h0, u32 h1)
 {
-    u32 r0, r1, k;
-    asm("sub.cc.u32 %0, %3, %5;\n\t"
-        "subc.cc.u32 %1, %4, 0;\n\t"
-        "subc.u32 %2, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, %2;\n\t"
-        "subc.u32 %1, %1, 0;\n\t"
-        "mad.lo.cc.u32 %0, %6, 0xffffffff, %0;\n\t"
-        "madc.hi.cc.u32 %1, %6, 0xffffffff, %1;\n\t"
-        "addc.u32 %2, 0, 0;\n\t"              // carry as 0/1 (an add-chain flag must be read by addc: ptxas keeps
-        "sub.cc.u32 %0, %0, %2;\n\t"          // subtraction borrows in the inverted sense, so never mix the two)
-        "subc.u32 %1, %1, 0;\n\t"             // + carry * eps = - carry + carry * 2^32
-        "add.u32 %1, %1, %2;"
-        : "=&r"(r0), "=&r"(r1), "=&r"(k)
-        : "r"(l), "r"(m), "r"(h1), "r"(h0));
-    const bool ge = r1 == 0xffffffffu && r0 != 0u;
-    return ge ? (u64)(r0 - 1u) : pack(r0, r1);
+    u32 r0, r1, d0, d1, k;
+    asm("add.cc.u32 %1, %6, %7;\n\t"         // mu = m + h0
+        "addc.u32 %1, %1, 0;\n\t"            // + c (the flag is left untouched)
+        "addc.cc.u32 %2, %7, %8;\n\t"        // d = h0 + h1 + c
+        "addc.u32 %3, 0, 0;\n\t"
+        "sub.cc.u32 %0, %5, %2;\n\t"         // (r1 : r0) = (mu + c : l) - d
+        "subc.cc.u32 %1, %1, %3;\n\t"
+        "subc.u32 %4, 0, 0;\n\t"             // k = -borrow
+        "mad.lo.cc.u32 %0, %4, %4, %0;\n\t"  // + borrow * p (see ff_sub)
+        "madc.hi.u32 %1, %4, %4, %1;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(d0), "=&r"(d1), "=&r"(k)
+        : "r"(l), "r"(m), "r"(h0), "r"(h1));
+    return ff_canon_dev(r0, r1 - k);
 }
 #endif
 
@@ -297,56 +318,42 @@ NB_D void mulwide(u32 a, u32 b, u32 &lo, u32 &hi)
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
     lo = lo32(t); hi = hi32(t);
 }
-// w + u mod p for w any 64-bit value and u < 2^63 + 2^32: one conditional subtraction of p
-NB_D u64 ff_add_loose_small(u32 w0, u32 w1, u32 u0, u32 u1)
-{
-    u32 r0, r1, t0, t1, k;
-    asm("add.cc.u32 %0, %5, %7;\n\t"
-        "addc.cc.u32 %1, %6, %8;\n\t"
-        "addc.u32 %4, 0, 0;\n\t"
-        "add.cc.u32 %2, %0, 0xffffffff;\n\t"
-        "addc.cc.u32 %3, %1, 0;\n\t"
-        "addc.u32 %4, %4, 0;"
-        : "=&r"(r0), "=&r"(r1), "=&r"(t0), "=&r"(t1), "=&r"(k)
-        : "r"(w0), "r"(w1), "r"(u0), "r"(u1));
-    return k ? pack(t0, t1) : pack(r0, r1);
-}
 // pattern a: (y0 - y2) + (y1 + y2) phi = pack(y0, y1) + y2 * eps.  The product and the 64-bit accumulate are one
-// mad.lo.cc / madc.hi.cc chain (carry on the FMA pipe); y2 * eps < 2^63, so one conditional subtraction of p.
+// mad.lo.cc / madc.hi.cc chain (carry on the FMA pipe).  y2 * eps < 2^63, so the sum is < 2^64 + 2^63: a carry
+// folds as + eps (no second carry, result < p); without a carry the sum may exceed p.  The two cases exclude each
+// other, so they share one IMAD.WIDE: + (carry | sum > p) * eps.
 NB_D u64 ff_comb_a(u32 y0, u32 y1, u32 y2)
 {
-    u32 r0, r1, t0, t1, k;
-    asm("mad.lo.cc.u32 %0, %7, 0xffffffff, %5;\n\t"
-        "madc.hi.cc.u32 %1, %7, 0xffffffff, %6;\n\t"
-        "addc.u32 %4, 0, 0;\n\t"
-        "add.cc.u32 %2, %0, 0xffffffff;\n\t"
+    u32 r0, r1, k, f;
+    asm("mad.lo.cc.u32 %0, %6, %7, %4;\n\t"
+        "madc.hi.cc.u32 %1, %6, %7, %5;\n\t"
+        "addc.u32 %2, 0, 0;\n\t"
+        "add.cc.u32 %3, %0, 0xfffffffe;\n\t"
         "addc.cc.u32 %3, %1, 0;\n\t"
-        "addc.u32 %4, %4, 0;"
-        : "=&r"(r0), "=&r"(r1), "=&r"(t0), "=&r"(t1), "=&r"(k)
-        : "r"(y0), "r"(y1), "r"(y2));
-    return k ? pack(t0, t1) : pack(r0, r1);
+        "addc.u32 %2, %2, 0;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(k), "=&r"(f)
+        : "r"(y0), "r"(y1), "r"(y2), "r"(nb_c_eps));
+    (void)f;
+    return ff_add_keps(r0, r1, k);
 }
-// pattern b: (-y1 - y2) + (y0 + y1) phi = y0 * 2^32 + y1 * eps - y2
+// pattern b: (-y1 - y2) + (y0 + y1) phi.  The carry c of s = y0 + y1 is c phi^2 = c phi - c and s + c cannot
+// overflow, so the value is the 64-bit difference ((s + c) : 0) - (y1 + y2 + c) in [-2^33, p - 1]: one borrow
+// fix (as in ff_sub) and the result is canonical without a compare.
 NB_D u64 ff_comb_b(u32 y0, u32 y1, u32 y2)
 {
-    u32 lo, hi, k, ks;
-    asm("mad.lo.cc.u32 %0, %4, 0xffffffff, 0;\n\t"     // lo = low(y1 * eps)
-        "madc.hi.cc.u32 %1, %4, 0xffffffff, %3;\n\t"   // hi = high(y1 * eps) + y0
-        "addc.u32 %2, 0, 0;\n\t"                       // k = carry
-        "sub.cc.u32 %0, %0, %5;\n\t"                   // - y2
-        "subc.cc.u32 %1, %1, 0;\n\t"
-        "subc.u32 %2, %2, 0;"                            // k in {-1, 0, 1}; -1 only when y0 = y1 = 0 < y2
-        : "=&r"(lo), "=&r"(hi), "=&r"(k)
+    u32 r0, r1, d0, d1, k;
+    asm("add.cc.u32 %1, %5, %6;\n\t"         // s = y0 + y1
+        "addc.u32 %1, %1, 0;\n\t"            // + c (flag untouched)
+        "addc.cc.u32 %2, %6, %7;\n\t"        // d = y1 + y2 + c
+        "addc.u32 %3, 0, 0;\n\t"
+        "sub.cc.u32 %0, 0, %2;\n\t"          // (r1 : r0) = ((s + c) : 0) - d
+        "subc.cc.u32 %1, %1, %3;\n\t"
+        "subc.u32 %4, 0, 0;\n\t"             // k = -borrow
+        "mad.lo.cc.u32 %0, %4, %4, %0;\n\t"  // + borrow * p
+        "madc.hi.u32 %1, %4, %4, %1;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(d0), "=&r"(d1), "=&r"(k)
         : "r"(y0), "r"(y1), "r"(y2));
-    // fold k * 2^64 = k * eps: (hi:lo) - k + k * 2^32 (two's complement k)
-    ks = (u32)((i32)k >> 31);
-    asm("sub.cc.u32 %0, %0, %2;\n\t"
-        "subc.u32 %1, %1, %3;\n\t"
-        "add.u32 %1, %1, %2;"
-        : "+r"(lo), "+r"(hi) : "r"(k), "r"(ks));
-    // k = +-1 leaves a canonical value; k = 0 may leave [p, 2^64)
-    const bool ge = hi == 0xffffffffu && lo != 0u;
-    return ge ? (u64)(lo - 1u) : pack(lo, hi);
+    return pack(r0, r1 - k);
 }
 // pattern c: (-y0 - y1) + (y0 - y2) phi = y0 * eps - pack(y1, y2);  pack(y1, y2) < 2^63
 NB_D u64 ff_comb_c(u32 y0, u32 y1, u32 y2)

@@ -58,9 +58,17 @@ template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dit_inlane
             constexpr int blk = q / half, k = q % half;
             constexpr int i0 = BASE + (blk * 2 * half + k) * STRIDE, i1 = i0 + half * STRIDE;
             constexpr int e = (ROOTLOG * k * (1 << s)) % 192;
-            u64 a = v[i0], t = ff_shl<(192 - e) % 192>(v[i1]);
-            v[i0] = ff_add(a, t);
-            v[i1] = ff_sub(a, t);
+            // inverse twiddle 2^-e = -2^(96 - e) for 0 < e < 96: shift by the positive amount and swap the two
+            // outputs instead of negating the product
+            if constexpr (e > 0 && e < 96) {
+                u64 a = v[i0], t = ff_shl<96 - e>(v[i1]);
+                v[i0] = ff_sub(a, t);
+                v[i1] = ff_add(a, t);
+            } else {
+                u64 a = v[i0], t = ff_shl<(192 - e) % 192>(v[i1]);
+                v[i0] = ff_add(a, t);
+                v[i1] = ff_sub(a, t);
+            }
         });
         NB_LOCKSTEP();
     });

@@ -7,7 +7,23 @@ using namespace nb;
 
 __constant__ unsigned c_one = 1, c_m1 = 0xffffffffu, c_eps32 = 0xffffffffu;
 
-// V1: current
+// V0: the 5-instruction borrow chain used until r1 v2.3 (four of the five tied to the ALU pipe)
+struct V0 {
+    static __device__ __forceinline__ u64 sub(u64 a, u64 b)
+    {
+        u32 l, h, m;
+        asm("sub.cc.u32 %0, %3, %5;\n\t"
+            "subc.cc.u32 %1, %4, %6;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, %2;\n\t"
+            "subc.u32 %1, %1, 0;"
+            : "=&r"(l), "=&r"(h), "=&r"(m)
+            : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+        return pack(l, h);
+    }
+    static __device__ __forceinline__ u64 add(u64 a, u64 b) { return sub(a, FF_P - b); }
+};
+// V1: current ff.cuh (borrow fix as one IMAD.WIDE)
 struct V1 { static __device__ __forceinline__ u64 sub(u64 a, u64 b) { return ff_sub(a, b); }
             static __device__ __forceinline__ u64 add(u64 a, u64 b) { return ff_add(a, b); } };
 // V2: plain C, compare-based
@@ -141,7 +157,8 @@ int main()
 {
     u64 *io; long long *dcyc;
     cudaMalloc(&io, 148 * 512 * 16 * 8); cudaMemset(io, 0x5a, 148 * 512 * 16 * 8); cudaMalloc(&dcyc, 8);
-    run<V1>("V1 carry-chain PTX (current)", io, dcyc);
+    run<V0>("V0 5-instruction borrow chain (old)", io, dcyc);
+    run<V1>("V1 IMAD.WIDE borrow fix (current)", io, dcyc);
     run<V2>("V2 plain C compare/select", io, dcyc);
     run<V3>("V3 IMAD.WIDE sub + predicated fix", io, dcyc);
     run<V4>("V4 no reduction (lower bound)", io, dcyc);

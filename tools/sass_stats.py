@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""Static per-phase / per-pipe instruction counts of the fused bootstrap kernel, from the SASS of the built
+library (no GPU needed).  The kernel is bound by the integer ALU pipe, so the ALU column of the step loop is
+the number that predicts its run time; use this to judge an arithmetic change before spending GPU minutes.
+
+    python tools/sass_stats.py [--kernel blind_rotate_kernel] [--by-func] [--lib path/to/lib.so]
+
+Each SASS instruction is attributed (through nvdisasm's inline chains, the library is built with -lineinfo)
+to the line of `br2_step` in kernels.cuh that called it, i.e. to a phase.  Counts are static: fwd1 / fwd2 /
+fwd3 are multiplied by their two sweeps per step (the `it` loops are not unrolled), the MAC by its two row
+iterations, and code inside the warp-uniform `switch (g)` of fwd2 / inv2 counts a quarter -- see `per step`.
+"""
+import argparse
+import collections
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+ALU = ('IADD3', 'IADD', 'LOP3', 'SHF', 'SEL', 'ISETP', 'PRMT', 'VIADD', 'LEA', 'IMNMX', 'VIMNMX', 'MOV', 'PLOP3', 'P2R',
+       'R2P', 'IABS', 'FLO', 'POPC', 'BREV', 'SGXT', 'BMSK', 'LOP', 'FSEL', 'FMNMX', 'CS2R', 'VABSDIFF', 'FSETP', 'I2FP')
+FMA = ('IMAD', 'FFMA', 'FMUL', 'FADD', 'HFMA2', 'IDP')
+LSU = ('LDS', 'STS', 'LDG', 'STG', 'LD', 'ST', 'LDSM', 'ATOMS', 'ATOMG', 'RED', 'LDC', 'LDCU', 'UBLKCP', 'SYNCS')
+UNI = ('UMOV', 'UIADD3', 'ULEA', 'ULOP3', 'UISETP', 'USHF', 'UIMAD', 'S2UR', 'UPLOP3', 'USEL', 'UPRMT', 'R2UR', 'UFLO',
+       'UP2UR', 'UIADD')
+
+
+def pipe_of(op):
+    base = op.split('.')[0]
+    if base in ALU:
+        return 'alu'
+    if base in FMA:
+        return 'fma'
+    if base in LSU:
+        return 'lsu'
+    if base in UNI:
+        return 'uni'
+    return 'other'
+
+
+def enclosing_functions(path):
+    """line -> name of the enclosing function (rough: last line that looks like a definition at depth <= 1)."""
+    names = {}
+    cur = None
+    rx = re.compile(r'^\s*(?:template\s*<[^>]*>\s*)?(?:NB_HD|NB_D|NB_HDC|__global__|__device__)\b.*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(')
+    try:
+        with open(path) as f:
+            for i, line in enumerate(f, 1):
+                m = rx.match(line)
+                if m:
+                    cur = m.group(1)
+                names[i] = cur
+    except OSError:
+        pass
+    return names
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--lib', default=os.path.join(ROOT, 'nufhe_b200', 'csrc', 'libnufhe_b200.so'))
+    ap.add_argument('--kernel', default='blind_rotate_kernel')
+    ap.add_argument('--by-func', action='store_true', help='also split each phase by innermost ff.cuh / br_phases function')
+    args = ap.parse_args()
+
+    tmp = tempfile.mkdtemp()
+    subprocess.check_call(['cuobjdump', '-xelf', 'all', args.lib], cwd=tmp, stdout=subprocess.DEVNULL)
+    cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
+    text = subprocess.run(['nvdisasm', '--print-line-info-inline', '-c', os.path.join(tmp, cubin)],
+                          capture_output=True, text=True).stdout.splitlines()
+
+    # phase = line of kernels.cuh inside br2_step
+    kpath = os.path.join(ROOT, 'nufhe_b200', 'csrc', 'kernels.cuh')
+    ksrc = open(kpath).read().splitlines()
+    phase_lines = {}
+    in_step = False
+    for i, line in enumerate(ksrc, 1):
+        if 'void br2_step' in line:
+            in_step = True
+        if in_step:
+            m = re.search(r'(phase_[a-z0-9_]+)', line)
+            if m:
+                phase_lines[i] = m.group(1)
+            if line.startswith('}'):
+                in_step = False
+    step_call_lines = [i for i, l in enumerate(ksrc, 1) if 'br2_step<true>' in l and 'void' not in l]
+
+    # lines of br_phases.cuh inside a `switch (g)` (warp-uniform 4-way): each branch runs for a quarter of the warps
+    bpath = os.path.join(ROOT, 'nufhe_b200', 'csrc', 'br_phases.cuh')
+    case_lines = {i for i, l in enumerate(open(bpath).read().splitlines(), 1) if re.match(r'\s*(case \d+|default):', l)}
+
+    fn_maps = {}
+
+    def fn_of(path, line):
+        if path not in fn_maps:
+            fn_maps[path] = enclosing_functions(path)
+        return fn_maps[path].get(line)
+
+    in_kernel = False
+    chain = []
+    counts = collections.defaultdict(lambda: collections.Counter())
+    byfunc = collections.defaultdict(lambda: collections.Counter())
+    rx_line = re.compile(r'//## File "([^"]+)", line (\d+)')
+    rx_ins = re.compile(r'^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)')
+    for ln in text:
+        if ln.startswith('.text.'):
+            in_kernel = args.kernel in ln
+            chain = []
+            continue
+        if not in_kernel:
+            continue
+        m = rx_line.search(ln)
+        if m:
+            if not chain or chain_done:
+                chain = []
+                chain_done = False
+            chain.append((m.group(1), int(m.group(2))))
+            continue
+        m = rx_ins.match(ln)
+        if not m:
+            continue
+        chain_done = True
+        op = m.group(1)
+        pipe = pipe_of(op)
+        phase = 'other'
+        in_loop = False
+        for path, line in chain:
+            if path.endswith('kernels.cuh'):
+                if line in phase_lines:
+                    phase = phase_lines[line]
+                if line in step_call_lines:
+                    in_loop = True
+        if phase != 'other' and not in_loop:
+            phase = 'plain:' + phase     # the non-rotating instantiation (nb_external_product)
+        w = 0.25 if any(path.endswith('br_phases.cuh') and line in case_lines for path, line in chain) else 1
+        counts[phase][pipe] += w
+        if args.by_func and chain:
+            inner = None
+            for path, line in chain:
+                f = fn_of(path, line)
+                if f and (path.endswith('ff.cuh')):
+                    inner = f
+                    break
+            if inner is None:
+                inner = fn_of(*chain[0]) or '?'
+            byfunc[phase][(inner, pipe)] += w
+
+    mult = {'phase_fwd1': 2, 'phase_fwd2': 2, 'phase_fwd3': 2, 'phase_mac': 2}
+    print('%-22s %7s %7s %7s %7s %7s %8s' % ('phase (static)', 'alu', 'fma', 'lsu', 'uni', 'other', 'total'))
+    tot = collections.Counter()
+    for phase in sorted(counts):
+        c = counts[phase]
+        print('%-22s %7d %7d %7d %7d %7d %8d' % (phase, c['alu'], c['fma'], c['lsu'], c['uni'], c['other'], sum(c.values())))
+        if phase.startswith('phase_'):
+            for k, v in c.items():
+                tot[k] += v * mult.get(phase, 1)
+    print('%-22s %7d %7d %7d %7d %7d %8d   (sweeps, MAC rows and switch weights applied)' % (
+        'per step, per thread', tot['alu'], tot['fma'], tot['lsu'], tot['uni'], tot['other'], sum(tot.values())))
+    if args.by_func:
+        for phase in sorted(byfunc):
+            if not phase.startswith('phase_'):
+                continue
+            print('--', phase)
+            agg = collections.defaultdict(collections.Counter)
+            for (fn, pipe), v in byfunc[phase].items():
+                agg[fn][pipe] += v
+            for fn, c in sorted(agg.items(), key=lambda kv: -sum(kv[1].values())):
+                print('   %-24s alu %6d  fma %6d  lsu %5d  other %5d' % (fn, c['alu'], c['fma'], c['lsu'], c['uni'] + c['other']))
+
+
+if __name__ == '__main__':
+    sys.exit(main())
