@@ -30,6 +30,17 @@
 #define NB_LOCKSTEP() ((void)0)
 #endif
 
+// experiment knobs (tools/variant_experiment.sh): how ff_sub folds its borrow and how x << r is split into limbs
+#ifndef NB_SUB_MODE
+#define NB_SUB_MODE 0
+#endif
+#ifndef NB_ADD_MODE
+#define NB_ADD_MODE NB_SUB_MODE
+#endif
+#ifndef NB_SHIFT_MODE
+#define NB_SHIFT_MODE 0
+#endif
+
 namespace nb {
 
 typedef uint64_t u64;
@@ -58,24 +69,54 @@ NB_HD u64 pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
 // x in [0, 2^64) -> canonical (arithmetic.mako:164-194 `mod`)
 NB_HD u64 ff_canon(u64 x) { return x >= FF_P ? x - FF_P : x; }
 
+#if defined(__CUDA_ARCH__)
+// a - b mod 2^64, minus eps when that borrowed.  MODE selects how the borrow is folded: 0 = second borrow chain
+// (ALU pipe), 1 = one IMAD.WIDE: d + m * m = d + borrow * (1 - 2^33), then hi -= m (m = -borrow), 2 = add chain.
+template <int MODE> NB_D u64 ff_sub_dev(u64 a, u64 b)
+{
+    if constexpr (MODE == 1) {
+        u32 l, h, m;
+        asm("sub.cc.u32 %0, %3, %5;\n\t"
+            "subc.cc.u32 %1, %4, %6;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "mad.lo.cc.u32 %0, %2, %2, %0;\n\t"
+            "madc.hi.u32 %1, %2, %2, %1;"
+            : "=&r"(l), "=&r"(h), "=&r"(m)
+            : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+        return pack(l, h - m);
+    } else if constexpr (MODE == 2) {
+        u32 l, h, m, be;
+        asm("sub.cc.u32 %0, %4, %6;\n\t"
+            "subc.cc.u32 %1, %5, %7;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "sub.u32 %3, 0, %2;\n\t"
+            "add.cc.u32 %0, %0, %3;\n\t"
+            "addc.u32 %1, %1, %2;"
+            : "=&r"(l), "=&r"(h), "=&r"(m), "=&r"(be)
+            : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+        (void)be;
+        return pack(l, h);
+    } else {
+        u32 l, h, m;
+        asm("sub.cc.u32 %0, %3, %5;\n\t"
+            "subc.cc.u32 %1, %4, %6;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, %2;\n\t"
+            "subc.u32 %1, %1, 0;"
+            : "=&r"(l), "=&r"(h), "=&r"(m)
+            : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+        (void)m;
+        return pack(l, h);
+    }
+}
+#endif
+
 // a - b mod p; a may be any 64-bit value, b canonical; result canonical iff a canonical.
 // (arithmetic.mako:122-161 `sub`): wrap-around of 2^64 is undone by subtracting 2^32-1.
 NB_HD u64 ff_sub(u64 a, u64 b)
 {
 #if defined(__CUDA_ARCH__)
-    // d = a - b mod 2^64 with borrow; the fix "- borrow * eps" runs on the FMA pipe: with m = -borrow (0 or
-    // 2^32 - 1), d + m * m = d + borrow * (1 - 2^33) is ONE IMAD.WIDE with a 64-bit addend (ptxas fuses the
-    // mad.lo.cc / madc.hi pair), and hi -= m adds borrow * 2^32.  Only the first two instructions are tied to
-    // the ALU pipe (the binding one, profiles/r1_final_summary.txt); the old 5-instruction borrow chain had four.
-    u32 l, h, m;
-    asm("sub.cc.u32 %0, %3, %5;\n\t"
-        "subc.cc.u32 %1, %4, %6;\n\t"
-        "subc.u32 %2, 0, 0;\n\t"
-        "mad.lo.cc.u32 %0, %2, %2, %0;\n\t"
-        "madc.hi.u32 %1, %2, %2, %1;"
-        : "=&r"(l), "=&r"(h), "=&r"(m)
-        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
-    return pack(l, h - m);
+    return ff_sub_dev<NB_SUB_MODE>(a, b);
 #else
     u64 d = a - b;
     return a < b ? d - FF_EPS : d;
@@ -85,7 +126,14 @@ NB_HD u64 ff_sub(u64 a, u64 b)
 NB_HD u64 ff_neg(u64 a) { return a ? FF_P - a : 0; }
 
 // a + b mod p, both canonical (arithmetic.mako:78-119 `add`), computed as a - (p - b).
-NB_HD u64 ff_add(u64 a, u64 b) { return ff_sub(a, FF_P - b); }
+NB_HD u64 ff_add(u64 a, u64 b)
+{
+#if defined(__CUDA_ARCH__)
+    return ff_sub_dev<NB_ADD_MODE>(a, FF_P - b);
+#else
+    return ff_sub(a, FF_P - b);
+#endif
+}
 
 // v * (2^32 - 1) for a 32-bit v: always canonical ((2^32-1)^2 < p).
 NB_HD u64 ff_eps_mul(u32 v)
@@ -375,10 +423,16 @@ template <int S> NB_D u64 ff_shl_dev(u64 x)
     u32 y0, y1, y2;
     if (r == 0) { y0 = lo32(x); y1 = hi32(x); y2 = 0; }
     else {
+#if NB_SHIFT_MODE == 1
+        y0 = lo32(x) << r;
+        y1 = (hi32(x) << r) | (lo32(x) >> (32 - r));
+        y2 = hi32(x) >> (32 - r);
+#else
         u32 c, z;
         mulwide(lo32(x), nb_c_pow2[r], y0, c);
         mulwide(hi32(x), nb_c_pow2[r], z, y2);
         y1 = z | c;
+#endif
     }
     if (q == 0) { u64 v = ff_comb_a(y0, y1, y2); return negate ? FF_P - v : v; }
     if (q == 1) { u64 v = ff_comb_b(y0, y1, y2); return negate ? FF_P - v : v; }

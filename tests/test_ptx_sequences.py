@@ -42,9 +42,16 @@ def run(fn, index=0, **variables):
 
 
 # ---- mirrors of the C glue ------------------------------------------------------------------------
-def ff_sub(a, b):
-    e = run('ff_sub', a=a, b=b)
-    return HELPERS['pack'](e['l'], (e['h'] - e['m']) & M32)
+SUB_MODE = 0          # which borrow fold ff_sub_dev<MODE> the mirrors below go through (all three are tested)
+_SUB_BLOCK = {1: 0, 2: 1, 0: 2}   # order of the asm blocks inside ff_sub_dev
+
+
+def ff_sub(a, b, mode=None):
+    mode = SUB_MODE if mode is None else mode
+    e = run('ff_sub_dev', _SUB_BLOCK[mode], a=a, b=b)
+    if mode == 1:
+        return HELPERS['pack'](e['l'], (e['h'] - e['m']) & M32)
+    return HELPERS['pack'](e['l'], e['h'])
 
 
 def ff_add(a, b):
@@ -151,7 +158,7 @@ def in_range(v):
 
 
 def test_parser_sees_every_device_sequence():
-    for fn, n in (('ff_sub', 1), ('mul128', 1), ('mac128', 1), ('ff_add_keps', 1), ('ff_canon_dev', 1),
+    for fn, n in (('ff_sub_dev', 3), ('mul128', 1), ('mac128', 1), ('ff_add_keps', 1), ('ff_canon_dev', 1),
                   ('ff_reduce_limbs', 1), ('ff_comb_a', 1), ('ff_comb_b', 1), ('mulwide', 1)):
         assert len(blocks(fn)) == n, fn
 
@@ -163,13 +170,14 @@ def test_carry_flag_families_are_never_mixed():
 
 
 def test_sub_add_all_edge_pairs():
-    for a in EDGE64 + LOOSE64:
-        for b in EDGE64:
-            got = ff_sub(a, b)
-            want = a - b if a >= b else a - b + P          # exact, no further reduction (a may be loose)
-            assert got == want, (hex(a), hex(b), hex(got), hex(want))
-            if a <= P:
-                assert in_range(got)
+    for mode in (0, 1, 2):
+        for a in EDGE64 + LOOSE64:
+            for b in EDGE64:
+                got = ff_sub(a, b, mode)
+                want = a - b if a >= b else a - b + P          # exact, no further reduction (a may be loose)
+                assert got == want, (mode, hex(a), hex(b), hex(got), hex(want))
+                if a <= P:
+                    assert in_range(got)
     for a in EDGE64:
         for b in EDGE64:
             got = ff_add(a, b)

@@ -41,6 +41,24 @@ def pipe_of(op):
     return 'other'
 
 
+COST = {'IMAD.WIDE(+R64)': 4, 'IMAD.WIDE(+RZ)': 4}
+STEP_MULT = {'phase_fwd1': 2, 'phase_fwd2': 2, 'phase_fwd3': 2, 'phase_mac': 2}
+
+
+def instruction_form(op, rest):
+    """Opcode with the distinctions that matter for issue cost: carry-out predicates, 64-bit addends."""
+    carry_out = bool(re.match(r'\s*R\w+, P\d', rest))
+    if op.startswith('IMAD.WIDE'):
+        key = 'IMAD.WIDE(+RZ)' if rest.rstrip(' ;').endswith('RZ') else 'IMAD.WIDE(+R64)'
+    elif op.startswith('IADD3'):
+        key = 'IADD3.X' if '.X' in op else 'IADD3'
+    elif op.startswith('IMAD.HI'):
+        key = 'IMAD.HI'
+    else:
+        key = re.sub(r'\.(LUT|U32|AND|OR|EX|GE|GT|LT|LE|NE|EQ|W|L|R|HI|64|128|E|CONSTANT|RECONVERGENT)\b', '', op)
+    return key + ('.P' if carry_out and key.startswith(('IMAD', 'IADD3')) else '')
+
+
 def enclosing_functions(path):
     """line -> name of the enclosing function (rough: last line that looks like a definition at depth <= 1)."""
     names = {}
@@ -63,10 +81,11 @@ def main():
     ap.add_argument('--lib', default=os.path.join(ROOT, 'nufhe_b200', 'csrc', 'libnufhe_b200.so'))
     ap.add_argument('--kernel', default='blind_rotate_kernel')
     ap.add_argument('--by-func', action='store_true', help='also split each phase by innermost ff.cuh / br_phases function')
+    ap.add_argument('--opcodes', action='store_true', help='per-step histogram of instruction forms (carry-out variants split)')
     args = ap.parse_args()
 
     tmp = tempfile.mkdtemp()
-    subprocess.check_call(['cuobjdump', '-xelf', 'all', args.lib], cwd=tmp, stdout=subprocess.DEVNULL)
+    subprocess.check_call(['cuobjdump', '-xelf', 'all', os.path.abspath(args.lib)], cwd=tmp, stdout=subprocess.DEVNULL)
     cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
     text = subprocess.run(['nvdisasm', '--print-line-info-inline', '-c', os.path.join(tmp, cubin)],
                           capture_output=True, text=True).stdout.splitlines()
@@ -103,7 +122,8 @@ def main():
     counts = collections.defaultdict(lambda: collections.Counter())
     byfunc = collections.defaultdict(lambda: collections.Counter())
     rx_line = re.compile(r'//## File "([^"]+)", line (\d+)')
-    rx_ins = re.compile(r'^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)')
+    rx_ins = re.compile(r'^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)(.*)')
+    forms = collections.Counter()
     for ln in text:
         if ln.startswith('.text.'):
             in_kernel = args.kernel in ln
@@ -136,6 +156,8 @@ def main():
             phase = 'plain:' + phase     # the non-rotating instantiation (nb_external_product)
         w = 0.25 if any(path.endswith('br_phases.cuh') and line in case_lines for path, line in chain) else 1
         counts[phase][pipe] += w
+        if args.opcodes and phase.startswith('phase_'):
+            forms[instruction_form(op, m.group(2))] += w * STEP_MULT.get(phase, 1)
         if args.by_func and chain:
             inner = None
             for path, line in chain:
@@ -147,7 +169,7 @@ def main():
                 inner = fn_of(*chain[0]) or '?'
             byfunc[phase][(inner, pipe)] += w
 
-    mult = {'phase_fwd1': 2, 'phase_fwd2': 2, 'phase_fwd3': 2, 'phase_mac': 2}
+    mult = STEP_MULT
     print('%-22s %7s %7s %7s %7s %7s %8s' % ('phase (static)', 'alu', 'fma', 'lsu', 'uni', 'other', 'total'))
     tot = collections.Counter()
     for phase in sorted(counts):
@@ -158,6 +180,17 @@ def main():
                 tot[k] += v * mult.get(phase, 1)
     print('%-22s %7d %7d %7d %7d %7d %8d   (sweeps, MAC rows and switch weights applied)' % (
         'per step, per thread', tot['alu'], tot['fma'], tot['lsu'], tot['uni'], tot['other'], sum(tot.values())))
+    if args.opcodes:
+        # issue cost in SMSP cycles per warp-instruction (tools/microbench/pipes.cu on B200): 2 on either integer
+        # pipe, except IMAD.WIDE with a 64-bit addend: 4
+        alu_c = sum(2 * v for k, v in forms.items() if pipe_of(k.split('(')[0]) == 'alu')
+        fma_c = sum((COST.get(k.replace('.P', ''), 2)) * v for k, v in forms.items() if pipe_of(k.split('(')[0]) == 'fma')
+        print('-- pipe cycles per step, per warp: ALU %.0f  FMA %.0f  (sum %.0f, balanced bound %.0f)' % (
+            alu_c, fma_c, alu_c + fma_c, (alu_c + fma_c) / 2))
+        print('-- instruction forms per step, per thread')
+        for k, v in sorted(forms.items(), key=lambda kv: -kv[1]):
+            if v >= 4:
+                print('   %-20s %7.0f' % (k, v))
     if args.by_func:
         for phase in sorted(byfunc):
             if not phase.startswith('phase_'):
