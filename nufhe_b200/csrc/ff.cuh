@@ -32,13 +32,19 @@
 
 // experiment knobs (tools/variant_experiment.sh): how ff_sub folds its borrow and how x << r is split into limbs
 #ifndef NB_SUB_MODE
-#define NB_SUB_MODE 0
+#define NB_SUB_MODE 2
 #endif
 #ifndef NB_ADD_MODE
 #define NB_ADD_MODE NB_SUB_MODE
 #endif
+#ifndef NB_KEPS_MODE
+#define NB_KEPS_MODE 0
+#endif
+#ifndef NB_FIX_MODE
+#define NB_FIX_MODE 0
+#endif
 #ifndef NB_SHIFT_MODE
-#define NB_SHIFT_MODE 0
+#define NB_SHIFT_MODE 1
 #endif
 
 namespace nb {
@@ -164,8 +170,9 @@ NB_HD u64 ff_reduce128(u64 lo, u64 hi)
 // pipe (the binding one, profiles/r1_final_summary.txt) sees a single SEL.
 NB_D void mul128(u64 a, u64 b, u32 &r0, u32 &r1, u32 &r2, u32 &r3)
 {
-    asm("mul.lo.u32 %0, %4, %6;\n\t"
-        "mul.hi.u32 %1, %4, %6;\n\t"
+    asm("{\n\t.reg .u64 t;\n\t"
+        "mul.wide.u32 t, %4, %6;\n\t"          // one IMAD.WIDE; a mul.lo / mul.hi pair costs IMAD + IMAD.HI (2 + 5 cycles)
+        "mov.b64 {%0, %1}, t;\n\t}\n\t"
         "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
         "madc.hi.u32 %2, %4, %7, 0;\n\t"
         "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
@@ -198,14 +205,23 @@ NB_D void mac128(u64 a, u64 b, u32 &c0, u32 &c1, u32 &c2, u32 &c3, u32 &c4)
         : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
         : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
 }
-// v + k * eps for k in {0, 1}: one IMAD.WIDE (the multiplier comes from the constant bank so that ptxas keeps
-// the multiply); used for "subtract p when v >= p" (v + eps wraps to v - p) and for carry folds.
+// v + k * eps for k in {0, 1}, as v - k + k * 2^32: one borrow-producing subtraction, the other two instructions
+// can go to either pipe.  (An IMAD.WIDE with a 64-bit addend would be a single instruction, but it issues at a
+// quarter of the IMAD rate and stalls the ALU pipe next to it: tools/microbench/pipes.cu)
+// Used for "subtract p when v > p" (v + eps wraps to v - p) and for carry folds.
 NB_D u64 ff_add_keps(u32 v0, u32 v1, u32 k)
 {
+#if NB_KEPS_MODE == 1
     asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
         "madc.hi.u32 %1, %2, %3, %1;"
         : "+r"(v0), "+r"(v1) : "r"(k), "r"(nb_c_eps));
     return pack(v0, v1);
+#else
+    asm("sub.cc.u32 %0, %0, %2;\n\t"
+        "subc.u32 %1, %1, 0;"
+        : "+r"(v0), "+r"(v1) : "r"(k));
+    return pack(v0, v1 + k);
+#endif
 }
 // any 64-bit v -> [0, p]: v - p if v > p (v = p is left alone: "almost canonical")
 NB_D u64 ff_canon_dev(u32 v0, u32 v1)
@@ -230,12 +246,22 @@ NB_D u64 ff_reduce_limbs(u32 l, u32 m, u32 h0, u32 h1)
         "addc.u32 %3, 0, 0;\n\t"
         "sub.cc.u32 %0, %5, %2;\n\t"         // (r1 : r0) = (mu + c : l) - d
         "subc.cc.u32 %1, %1, %3;\n\t"
+#if NB_FIX_MODE == 1
         "subc.u32 %4, 0, 0;\n\t"             // k = -borrow
-        "mad.lo.cc.u32 %0, %4, %4, %0;\n\t"  // + borrow * p (see ff_sub)
+        "mad.lo.cc.u32 %0, %4, %4, %0;\n\t"  // + borrow * p as IMAD.WIDE (ff_sub_dev<1>)
         "madc.hi.u32 %1, %4, %4, %1;"
         : "=&r"(r0), "=&r"(r1), "=&r"(d0), "=&r"(d1), "=&r"(k)
         : "r"(l), "r"(m), "r"(h0), "r"(h1));
     return ff_canon_dev(r0, r1 - k);
+#else
+        "subc.u32 %4, 0, 0;\n\t"             // k = -borrow
+        "sub.u32 %2, 0, %4;\n\t"             // borrow
+        "add.cc.u32 %0, %0, %2;\n\t"         // + borrow * p = (k : borrow)
+        "addc.u32 %1, %1, %4;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(d0), "=&r"(d1), "=&r"(k)
+        : "r"(l), "r"(m), "r"(h0), "r"(h1));
+    return ff_canon_dev(r0, r1);
+#endif
 }
 #endif
 
@@ -396,12 +422,22 @@ NB_D u64 ff_comb_b(u32 y0, u32 y1, u32 y2)
         "addc.u32 %3, 0, 0;\n\t"
         "sub.cc.u32 %0, 0, %2;\n\t"          // (r1 : r0) = ((s + c) : 0) - d
         "subc.cc.u32 %1, %1, %3;\n\t"
+#if NB_FIX_MODE == 1
         "subc.u32 %4, 0, 0;\n\t"             // k = -borrow
-        "mad.lo.cc.u32 %0, %4, %4, %0;\n\t"  // + borrow * p
+        "mad.lo.cc.u32 %0, %4, %4, %0;\n\t"  // + borrow * p as IMAD.WIDE (ff_sub_dev<1>)
         "madc.hi.u32 %1, %4, %4, %1;"
         : "=&r"(r0), "=&r"(r1), "=&r"(d0), "=&r"(d1), "=&r"(k)
         : "r"(y0), "r"(y1), "r"(y2));
     return pack(r0, r1 - k);
+#else
+        "subc.u32 %4, 0, 0;\n\t"             // k = -borrow
+        "sub.u32 %2, 0, %4;\n\t"             // borrow
+        "add.cc.u32 %0, %0, %2;\n\t"         // + borrow * p = (k : borrow)
+        "addc.u32 %1, %1, %4;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(d0), "=&r"(d1), "=&r"(k)
+        : "r"(y0), "r"(y1), "r"(y2));
+    return pack(r0, r1);
+#endif
 }
 // pattern c: (-y0 - y1) + (y0 - y2) phi = y0 * eps - pack(y1, y2);  pack(y1, y2) < 2^63
 NB_D u64 ff_comb_c(u32 y0, u32 y1, u32 y2)

@@ -55,6 +55,30 @@ def _operands(s):
     return res
 
 
+def preprocess(source, defines):
+    """Resolve `#if NAME == n` / `#else` / `#endif` groups whose NAME is in `defines` (other directives are kept)."""
+    out, stack = [], []
+    for line in source.split('\n'):
+        m = re.match(r'\s*#\s*if\s+(\w+)\s*==\s*(\d+)\s*$', line)
+        if m and m.group(1) in defines:
+            stack.append(defines[m.group(1)] == int(m.group(2)))
+            continue
+        if stack and re.match(r'\s*#\s*(if|ifdef|ifndef)\b', line):
+            stack.append(None)                       # unrelated nested group: transparent
+            out.append(line)
+            continue
+        if stack and re.match(r'\s*#\s*else\b', line) and stack[-1] is not None:
+            stack[-1] = not stack[-1]
+            continue
+        if stack and re.match(r'\s*#\s*endif\b', line):
+            if stack.pop() is None:
+                out.append(line)
+            continue
+        if all(v is not False for v in stack):
+            out.append(line)
+    return '\n'.join(out)
+
+
 def extract_asm_blocks(source, function):
     """All asm blocks inside the body of `function` (first definition found), in order."""
     m = re.search(r'\b%s\s*\([^)]*\)\s*\{' % re.escape(function), source)
@@ -123,21 +147,49 @@ class Machine:
             else:
                 vals.append(eval(expr, {}, env) & ((1 << w) - 1))
 
+        local = {}
+
         def get(tok):
             tok = tok.strip()
             if tok.startswith('%'):
                 v = vals[int(tok[1:])]
                 assert v is not None, 'operand %s read before it is written' % tok
                 return v
+            if tok in local:
+                assert local[tok] is not None, 'register %s read before it is written' % tok
+                return local[tok]
             return int(tok, 0) & M64
 
-        for ins in [i.strip() for i in block.text.split(';') if i.strip()]:
+        def put(tok, value, width):
+            tok = tok.strip()
+            if tok.startswith('%'):
+                assert widths[int(tok[1:])] == width, tok
+                vals[int(tok[1:])] = value
+            else:
+                assert tok in local, tok
+                local[tok] = value
+
+        text = block.text.replace('{', ' { ').replace('}', ' } ')
+        text = re.sub(r'\{\s*(%\d+|\w+)\s*,\s*(%\d+|\w+)\s*\}', r'<\1|\2>', text)      # vector operand {a, b}
+        text = text.replace('{', ';').replace('}', ';')                                # scopes: flat
+        for ins in [i.strip() for i in text.split(';') if i.strip()]:
+            m = re.match(r'\.reg\s+\.(\w+)\s+(.*)$', ins)
+            if m:
+                for name in m.group(2).split(','):
+                    local[name.strip()] = None
+                continue
+            m = re.match(r'mov\.b64\s+<(.+)\|(.+)>\s*,\s*(.+)$', ins)
+            if m:
+                v = get(m.group(3))
+                put(m.group(1), v & M32, 32)
+                put(m.group(2), v >> 32, 32)
+                continue
             m = re.match(r'([a-z0-9.]+)\s+(.*)$', ins)
             opc, args = m.group(1), [a.strip() for a in m.group(2).split(',')]
             parts = opc.split('.')
             base, cc = parts[0], 'cc' in parts
             assert parts[-1] in ('u32', 's32'), ins
-            d = int(args[0][1:])
+            d = args[0]
             if base in ('add', 'addc'):
                 r = get(args[1]) + get(args[2]) + (self._read_cf('add') if base == 'addc' else 0)
                 res, c, kind = r & M32, r >> 32, 'add'
@@ -151,10 +203,8 @@ class Machine:
                 res, c, kind = r & M32, r >> 32, 'add'
             elif base == 'mul' and 'wide' in parts:
                 res, c, kind = get(args[1]) * get(args[2]), None, None
-                assert widths[d] == 64
             elif base == 'mad' and 'wide' in parts:
                 res, c, kind = (get(args[1]) * get(args[2]) + get(args[3])) & M64, None, None
-                assert widths[d] == 64
             elif base == 'mul':
                 pr = get(args[1]) * get(args[2])
                 res, c, kind = ((pr & M32) if 'lo' in parts else (pr >> 32)), None, None
@@ -163,7 +213,7 @@ class Machine:
             if cc:
                 assert c is not None and c in (0, 1), ins
                 self.cf, self.cf_kind = c, kind
-            vals[d] = res
+            put(d, res, 64 if 'wide' in parts else 32)
         for idx, (cons, expr) in enumerate(block.outputs):
             assert re.match(r'^[A-Za-z_][A-Za-z0-9_]*$', expr), 'output %r is not a plain variable' % expr
             env[expr] = vals[idx]

@@ -11,10 +11,20 @@ import random
 
 import pytest
 
-from ptx_emul import Machine, extract_asm_blocks, M32, M64
+from ptx_emul import Machine, extract_asm_blocks, preprocess, M32, M64
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = open(os.path.join(ROOT, 'nufhe_b200', 'csrc', 'ff.cuh')).read()
+RAW = open(os.path.join(ROOT, 'nufhe_b200', 'csrc', 'ff.cuh')).read()
+
+
+def _default(name):
+    import re
+    return int(re.search(r'#define %s (\d+)' % name, RAW).group(1))
+
+
+# the build's defaults of the variant knobs (each alternative is also exercised below)
+KNOBS = {k: _default(k) for k in ('NB_KEPS_MODE', 'NB_FIX_MODE', 'NB_SHIFT_MODE')}
+SRC = preprocess(RAW, KNOBS)
 P = (1 << 64) - (1 << 32) + 1
 EPS = (1 << 32) - 1
 
@@ -42,7 +52,7 @@ def run(fn, index=0, **variables):
 
 
 # ---- mirrors of the C glue ------------------------------------------------------------------------
-SUB_MODE = 0          # which borrow fold ff_sub_dev<MODE> the mirrors below go through (all three are tested)
+SUB_MODE = _default('NB_SUB_MODE')          # which borrow fold ff_sub_dev<MODE> the mirrors below go through (all three are tested)
 _SUB_BLOCK = {1: 0, 2: 1, 0: 2}   # order of the asm blocks inside ff_sub_dev
 
 
@@ -60,7 +70,9 @@ def ff_add(a, b):
 
 def ff_add_keps(v0, v1, k):
     e = run('ff_add_keps', v0=v0, v1=v1, k=k)
-    return HELPERS['pack'](e['v0'], e['v1'])
+    if KNOBS['NB_KEPS_MODE'] == 1:
+        return HELPERS['pack'](e['v0'], e['v1'])
+    return HELPERS['pack'](e['v0'], (e['v1'] + k) & M32)
 
 
 def ff_canon_dev(v0, v1):
@@ -70,7 +82,9 @@ def ff_canon_dev(v0, v1):
 
 def ff_reduce_limbs(l, m, h0, h1):
     e = run('ff_reduce_limbs', l=l, m=m, h0=h0, h1=h1)
-    return ff_canon_dev(e['r0'], (e['r1'] - e['k']) & M32)
+    if KNOBS['NB_FIX_MODE'] == 1:
+        return ff_canon_dev(e['r0'], (e['r1'] - e['k']) & M32)
+    return ff_canon_dev(e['r0'], e['r1'])
 
 
 def mul128(a, b):
@@ -102,7 +116,9 @@ def ff_comb_a(y0, y1, y2):
 
 def ff_comb_b(y0, y1, y2):
     e = run('ff_comb_b', y0=y0, y1=y1, y2=y2)
-    return HELPERS['pack'](e['r0'], (e['r1'] - e['k']) & M32)
+    if KNOBS['NB_FIX_MODE'] == 1:
+        return HELPERS['pack'](e['r0'], (e['r1'] - e['k']) & M32)
+    return HELPERS['pack'](e['r0'], e['r1'])
 
 
 def ff_comb_c(y0, y1, y2, neg=False):
@@ -117,6 +133,8 @@ def ff_shl_dev(x, S):
     r, q = s96 % 32, s96 // 32
     if r == 0:
         y0, y1, y2 = x & M32, x >> 32, 0
+    elif KNOBS['NB_SHIFT_MODE'] == 1:
+        y0, y1, y2 = (x << r) & M32, (x >> (32 - r)) & M32, x >> (64 - r)
     else:
         y0, c = mulwide(x & M32, 1 << r)
         z, y2 = mulwide(x >> 32, 1 << r)
@@ -137,6 +155,23 @@ def ff_shl(x, S):
     if s == 96:
         return P - x
     return ff_shl_dev(x, S)
+
+
+@pytest.fixture(params=[None, {'NB_KEPS_MODE': 1}, {'NB_FIX_MODE': 1}, {'NB_SHIFT_MODE': 0}], autouse=True,
+                ids=['default', 'keps-wide', 'fix-wide', 'shift-mulwide'])
+def knobs(request):
+    """Every test runs with the default knobs and with each alternative code path selected."""
+    global SRC
+    saved = dict(KNOBS)
+    if request.param:
+        KNOBS.update({k: v for k, v in request.param.items()})
+    SRC = preprocess(RAW, KNOBS)
+    _BLOCKS.clear()
+    yield
+    KNOBS.clear()
+    KNOBS.update(saved)
+    SRC = preprocess(RAW, KNOBS)
+    _BLOCKS.clear()
 
 
 # ---- inputs -------------------------------------------------------------------------------------
