@@ -56,12 +56,12 @@ def _operands(s):
 
 
 def preprocess(source, defines):
-    """Resolve `#if NAME == n` / `#else` / `#endif` groups whose NAME is in `defines` (other directives are kept)."""
+    """Resolve `#if NAME == n` (or `#if NAME`) / `#else` / `#endif` groups whose NAME is in `defines` (other directives are kept)."""
     out, stack = [], []
     for line in source.split('\n'):
-        m = re.match(r'\s*#\s*if\s+(\w+)\s*==\s*(\d+)\s*$', line)
+        m = re.match(r'\s*#\s*if\s+(\w+)\s*(?:==\s*(\d+)\s*)?$', line)
         if m and m.group(1) in defines:
-            stack.append(defines[m.group(1)] == int(m.group(2)))
+            stack.append(defines[m.group(1)] == int(m.group(2)) if m.group(2) else bool(defines[m.group(1)]))
             continue
         if stack and re.match(r'\s*#\s*(if|ifdef|ifndef)\b', line):
             stack.append(None)                       # unrelated nested group: transparent
@@ -76,7 +76,20 @@ def preprocess(source, defines):
             continue
         if all(v is not False for v in stack):
             out.append(line)
-    return '\n'.join(out)
+    text = '\n'.join(out)
+    # function-like macros that build asm text (NB_ASM_*): expand the definitions that survived the #if groups
+    for m in re.finditer(r'#define (NB_ASM_\w+)\(([^)]*)\)[ \t]+(.*)', text):
+        name, params, body = m.group(1), [q.strip() for q in m.group(2).split(',')], m.group(3)
+
+        def expand(call, params=params, body=body):
+            args = [a.strip() for a in _split_top(call.group(1), ',')]
+            assert len(args) == len(params), call.group(0)
+            res = body
+            for prm, arg in zip(params, args):
+                res = re.sub(r'\b%s\b' % prm, lambda _m, arg=arg: arg, res)
+            return re.sub(r'"\s*"', '', res)          # adjacent literals concatenate
+        text = re.sub(r'(?<!#define )\b%s\(((?:[^()]|\([^()]*\))*)\)' % name, expand, text)
+    return text
 
 
 def extract_asm_blocks(source, function):

@@ -23,7 +23,7 @@ def _default(name):
 
 
 # the build's defaults of the variant knobs (each alternative is also exercised below)
-KNOBS = {k: _default(k) for k in ('NB_KEPS_MODE', 'NB_FIX_MODE', 'NB_SHIFT_MODE')}
+KNOBS = {k: _default(k) for k in ('NB_FMA_CARRY',)}
 SRC = preprocess(RAW, KNOBS)
 P = (1 << 64) - (1 << 32) + 1
 EPS = (1 << 32) - 1
@@ -33,6 +33,7 @@ HELPERS = {
     'hi32': lambda x: (x >> 32) & M32,
     'pack': lambda lo, hi: ((hi & M32) << 32) | (lo & M32),
     'nb_c_eps': EPS,
+    'nb_c_zero': 0,
     'nb_c_pow2': [1 << i for i in range(32)],
 }
 _BLOCKS = {}
@@ -52,38 +53,33 @@ def run(fn, index=0, **variables):
 
 
 # ---- mirrors of the C glue ------------------------------------------------------------------------
-SUB_MODE = _default('NB_SUB_MODE')          # which borrow fold ff_sub_dev<MODE> the mirrors below go through (all three are tested)
-_SUB_BLOCK = {1: 0, 2: 1, 0: 2}   # order of the asm blocks inside ff_sub_dev
-
-
-def ff_sub(a, b, mode=None):
-    mode = SUB_MODE if mode is None else mode
-    e = run('ff_sub_dev', _SUB_BLOCK[mode], a=a, b=b)
-    if mode == 1:
-        return HELPERS['pack'](e['l'], (e['h'] - e['m']) & M32)
+def ff_sub(a, b):
+    e = run('ff_sub', a=a, b=b)
     return HELPERS['pack'](e['l'], e['h'])
 
 
 def ff_add(a, b):
+    if KNOBS['NB_FMA_CARRY']:
+        e = run('ff_add', b=b)
+        return ff_sub(a, HELPERS['pack'](e['n0'], e['n1']))
     return ff_sub(a, (P - b) & M64)
 
 
-def ff_add_keps(v0, v1, k):
-    e = run('ff_add_keps', v0=v0, v1=v1, k=k)
-    if KNOBS['NB_KEPS_MODE'] == 1:
-        return HELPERS['pack'](e['v0'], e['v1'])
-    return HELPERS['pack'](e['v0'], (e['v1'] + k) & M32)
+def ff_add_meps(v0, v1, m):
+    e = run('ff_add_meps', v0=v0, v1=v1, m=m)
+    return HELPERS['pack'](e['v0'], e['v1'])
+
+
+def ff_gt_p_mask(v0, v1):
+    return run('ff_gt_p_mask', v0=v0, v1=v1)['m']
 
 
 def ff_canon_dev(v0, v1):
-    e = run('ff_canon_dev', v0=v0, v1=v1)
-    return ff_add_keps(v0, v1, e['f'])
+    return ff_add_meps(v0, v1, ff_gt_p_mask(v0, v1))
 
 
 def ff_reduce_limbs(l, m, h0, h1):
     e = run('ff_reduce_limbs', l=l, m=m, h0=h0, h1=h1)
-    if KNOBS['NB_FIX_MODE'] == 1:
-        return ff_canon_dev(e['r0'], (e['r1'] - e['k']) & M32)
     return ff_canon_dev(e['r0'], e['r1'])
 
 
@@ -111,13 +107,11 @@ def mulwide(a, b):
 
 def ff_comb_a(y0, y1, y2):
     e = run('ff_comb_a', y0=y0, y1=y1, y2=y2)
-    return ff_add_keps(e['r0'], e['r1'], e['k'])
+    return ff_add_meps(e['r0'], e['r1'], (e['m'] - e['k']) & M32)
 
 
 def ff_comb_b(y0, y1, y2):
     e = run('ff_comb_b', y0=y0, y1=y1, y2=y2)
-    if KNOBS['NB_FIX_MODE'] == 1:
-        return HELPERS['pack'](e['r0'], (e['r1'] - e['k']) & M32)
     return HELPERS['pack'](e['r0'], e['r1'])
 
 
@@ -133,12 +127,8 @@ def ff_shl_dev(x, S):
     r, q = s96 % 32, s96 // 32
     if r == 0:
         y0, y1, y2 = x & M32, x >> 32, 0
-    elif KNOBS['NB_SHIFT_MODE'] == 1:
-        y0, y1, y2 = (x << r) & M32, (x >> (32 - r)) & M32, x >> (64 - r)
     else:
-        y0, c = mulwide(x & M32, 1 << r)
-        z, y2 = mulwide(x >> 32, 1 << r)
-        y1 = z | c
+        y0, y1, y2 = (x << r) & M32, (x >> (32 - r)) & M32, x >> (64 - r)
     if q == 0:
         v = ff_comb_a(y0, y1, y2)
         return (P - v) if negate else v
@@ -157,8 +147,7 @@ def ff_shl(x, S):
     return ff_shl_dev(x, S)
 
 
-@pytest.fixture(params=[None, {'NB_KEPS_MODE': 1}, {'NB_FIX_MODE': 1}, {'NB_SHIFT_MODE': 0}], autouse=True,
-                ids=['default', 'keps-wide', 'fix-wide', 'shift-mulwide'])
+@pytest.fixture(params=[None, {'NB_FMA_CARRY': 0}], autouse=True, ids=['default', 'plain-addc'])
 def knobs(request):
     """Every test runs with the default knobs and with each alternative code path selected."""
     global SRC
@@ -193,7 +182,7 @@ def in_range(v):
 
 
 def test_parser_sees_every_device_sequence():
-    for fn, n in (('ff_sub_dev', 3), ('mul128', 1), ('mac128', 1), ('ff_add_keps', 1), ('ff_canon_dev', 1),
+    for fn, n in (('ff_sub', 1), ('mul128', 1), ('mac128', 1), ('ff_add_meps', 1), ('ff_gt_p_mask', 1),
                   ('ff_reduce_limbs', 1), ('ff_comb_a', 1), ('ff_comb_b', 1), ('mulwide', 1)):
         assert len(blocks(fn)) == n, fn
 
@@ -205,14 +194,13 @@ def test_carry_flag_families_are_never_mixed():
 
 
 def test_sub_add_all_edge_pairs():
-    for mode in (0, 1, 2):
-        for a in EDGE64 + LOOSE64:
-            for b in EDGE64:
-                got = ff_sub(a, b, mode)
-                want = a - b if a >= b else a - b + P          # exact, no further reduction (a may be loose)
-                assert got == want, (mode, hex(a), hex(b), hex(got), hex(want))
-                if a <= P:
-                    assert in_range(got)
+    for a in EDGE64 + LOOSE64:
+        for b in EDGE64:
+            got = ff_sub(a, b)
+            want = a - b if a >= b else a - b + P          # exact, no further reduction (a may be loose)
+            assert got == want, (hex(a), hex(b), hex(got), hex(want))
+            if a <= P:
+                assert in_range(got)
     for a in EDGE64:
         for b in EDGE64:
             got = ff_add(a, b)
@@ -222,12 +210,20 @@ def test_sub_add_all_edge_pairs():
         assert ff_add(a, b) % P == (a + b) % P and in_range(ff_add(a, b))
 
 
-def test_canon_and_keps():
+def test_canon_and_masked_eps():
     for v in EDGE64 + LOOSE64 + [RNG.randrange(1 << 64) for _ in range(500)]:
         got = ff_canon_dev(v & M32, v >> 32)
         assert got == (v - P if v > P else v), hex(v)
+        assert ff_gt_p_mask(v & M32, v >> 32) == (M32 if v > P else 0)
         for k in (0, 1):
-            assert ff_add_keps(v & M32, v >> 32, k) == (v + k * EPS) & M64
+            assert ff_add_meps(v & M32, v >> 32, k * M32) == (v + k * EPS) & M64
+
+
+def test_negation_inside_add():
+    for b in EDGE64 + rand_field(500):
+        if KNOBS['NB_FMA_CARRY']:
+            e = run('ff_add', b=b)
+            assert HELPERS['pack'](e['n0'], e['n1']) == P - b, hex(b)
 
 
 def test_reduce_limbs_all_edge_limbs():
