@@ -30,19 +30,6 @@
 #define NB_LOCKSTEP() ((void)0)
 #endif
 
-// NB_FMA_CARRY = 1 (default): a carry flag is turned into a register (or added to one) with `madc.lo d, z, z, x`
-// where z is a zero ptxas cannot see through (constant bank): that compiles to IMAD.X on the FMA pipe instead of
-// SEL / IADD3.X on the ALU pipe, the binding pipe of every kernel here.  0 = plain `addc` (for A/B runs).
-#ifndef NB_FMA_CARRY
-#define NB_FMA_CARRY 1
-#endif
-#if NB_FMA_CARRY
-#define NB_ASM_ADDC(d, x, z) "madc.lo.u32 " d ", " z ", " z ", " x ";\n\t"
-#else
-#define NB_ASM_ADDC(d, x, z) "addc.u32 " d ", " x ", 0;\n\t"
-#endif
-
-
 namespace nb {
 
 typedef uint64_t u64;
@@ -62,7 +49,6 @@ __constant__ u32 nb_c_pow2[32] = {
     1u << 21, 1u << 22, 1u << 23, 1u << 24, 1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30,
     1u << 31};
 __constant__ u32 nb_c_eps = 0xffffffffu;
-__constant__ u32 nb_c_zero = 0;          // see NB_FMA_CARRY
 #endif
 
 NB_HD u32 lo32(u64 x) { return (u32)x; }
@@ -78,10 +64,10 @@ NB_HD u64 ff_sub(u64 a, u64 b)
 {
 #if defined(__CUDA_ARCH__)
     // d = a - b mod 2^64; on a borrow add p = (m : beta) with beta = borrow, m = -borrow.  Three instructions are
-    // tied to the ALU pipe (the carry producers), the other three (m, beta, the last addc) compile to IMAD.X / IMAD.MOV.
-    // Measured alternatives (profiles/r1b_variants.md): a second borrow chain (4 ALU), and the fold as ONE IMAD.WIDE
-    // with a 64-bit addend, d + m * m then hi -= m -- fewest instructions, slowest: that form issues every 4 cycles and
-    // blocks the ALU pipe next to it.
+    // tied to the ALU pipe (the carry producers); m, beta and the last addc compile to IMAD.X / IMAD.MOV on the FMA
+    // pipe.  Measured alternatives (profiles/r1b_variants.md): a second borrow chain (4 ALU instructions, +6 %), and
+    // the fold as ONE IMAD.WIDE with a 64-bit addend (d + m * m, then hi -= m) -- fewest instructions, slowest:
+    // that form issues every 4 cycles and blocks the ALU pipe next to it (+8 %).
     u32 l, h, m, be;
     asm("sub.cc.u32 %0, %4, %6;\n\t"
         "subc.cc.u32 %1, %5, %7;\n\t"
@@ -102,23 +88,7 @@ NB_HD u64 ff_sub(u64 a, u64 b)
 NB_HD u64 ff_neg(u64 a) { return a ? FF_P - a : 0; }
 
 // a + b mod p, both canonical (arithmetic.mako:78-119 `add`), computed as a - (p - b).
-NB_HD u64 ff_add(u64 a, u64 b)
-{
-#if defined(__CUDA_ARCH__) && NB_FMA_CARRY
-    // p - b with one ALU instruction: t = -b0 - 1 (IMAD), n0 = t + 2 (carry = [b0 <= 1] = no borrow),
-    // n1 = -b1 - 2 + carry (IMAD.X).  The multiplier 2^32 - 1 comes from the constant bank so that the multiplies stay.
-    u32 n0, n1, t;
-    asm("mad.lo.u32 %2, %3, %5, %5;\n\t"
-        "add.cc.u32 %0, %2, 2;\n\t"
-        "madc.lo.u32 %1, %4, %5, 0xfffffffe;"
-        : "=&r"(n0), "=&r"(n1), "=&r"(t)
-        : "r"(lo32(b)), "r"(hi32(b)), "r"(nb_c_eps));
-    (void)t;
-    return ff_sub(a, pack(n0, n1));
-#else
-    return ff_sub(a, FF_P - b);
-#endif
-}
+NB_HD u64 ff_add(u64 a, u64 b) { return ff_sub(a, FF_P - b); }
 
 // v * (2^32 - 1) for a 32-bit v: always canonical ((2^32-1)^2 < p).
 NB_HD u64 ff_eps_mul(u32 v)
@@ -156,11 +126,11 @@ NB_D void mul128(u64 a, u64 b, u32 &r0, u32 &r1, u32 &r2, u32 &r3)
         "madc.hi.u32 %2, %4, %7, 0;\n\t"
         "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
         "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
-        NB_ASM_ADDC("%3", "0", "%8")
+        "addc.u32 %3, 0, 0;\n\t"
         "mad.lo.cc.u32 %2, %5, %7, %2;\n\t"
         "madc.hi.u32 %3, %5, %7, %3;"
         : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
-        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)), "r"(nb_c_zero));
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
 }
 // acc (5 limbs, acc4 small) += a * b
 NB_D void mac128(u64 a, u64 b, u32 &c0, u32 &c1, u32 &c2, u32 &c3, u32 &c4)
@@ -169,42 +139,42 @@ NB_D void mac128(u64 a, u64 b, u32 &c0, u32 &c1, u32 &c2, u32 &c3, u32 &c4)
         "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
         "addc.cc.u32 %2, %2, 0;\n\t"
         "addc.cc.u32 %3, %3, 0;\n\t"
-        NB_ASM_ADDC("%4", "%4", "%9")
+        "addc.u32 %4, %4, 0;\n\t"
         "mad.lo.cc.u32 %1, %5, %8, %1;\n\t"
         "madc.hi.cc.u32 %2, %5, %8, %2;\n\t"
         "addc.cc.u32 %3, %3, 0;\n\t"
-        NB_ASM_ADDC("%4", "%4", "%9")
+        "addc.u32 %4, %4, 0;\n\t"
         "mad.lo.cc.u32 %1, %6, %7, %1;\n\t"
         "madc.hi.cc.u32 %2, %6, %7, %2;\n\t"
         "addc.cc.u32 %3, %3, 0;\n\t"
-        NB_ASM_ADDC("%4", "%4", "%9")
+        "addc.u32 %4, %4, 0;\n\t"
         "mad.lo.cc.u32 %2, %6, %8, %2;\n\t"
         "madc.hi.cc.u32 %3, %6, %8, %3;\n\t"
-        NB_ASM_ADDC("%4", "%4", "%9")
+        "addc.u32 %4, %4, 0;"
         : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
-        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)), "r"(nb_c_zero));
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
 }
-// v + eps for a mask m = 2^32 - 1, v for m = 0 (mod 2^64): a 64-bit addition of (0 : m).  Used for "subtract p when
-// v > p" (v + eps wraps to v - p) and for carry folds.  One ALU instruction.
-NB_D u64 ff_add_meps(u32 v0, u32 v1, u32 m)
+// v + k * eps for k in {0, 1}, as v - k + k * 2^32: one borrow-producing subtraction, the other two instructions
+// can go to either pipe.  (An IMAD.WIDE with a 64-bit addend would be a single instruction, but it issues at a
+// quarter of the IMAD rate and stalls the ALU pipe next to it: tools/microbench/pipes.cu)
+// Used for "subtract p when v > p" (v + eps wraps to v - p) and for carry folds.
+NB_D u64 ff_add_keps(u32 v0, u32 v1, u32 k)
 {
-    asm("add.cc.u32 %0, %0, %2;\n\t"
-        NB_ASM_ADDC("%1", "%1", "%3")
-        : "+r"(v0), "+r"(v1) : "r"(m), "r"(nb_c_zero));
-    return pack(v0, v1);
-}
-// mask of [v > p]: the borrow of p - v
-NB_D u32 ff_gt_p_mask(u32 v0, u32 v1)
-{
-    u32 m;
-    asm("sub.cc.u32 %0, 1, %1;\n\t"
-        "subc.cc.u32 %0, 0xffffffff, %2;\n\t"
-        "subc.u32 %0, 0, 0;"
-        : "=&r"(m) : "r"(v0), "r"(v1));
-    return m;
+    asm("sub.cc.u32 %0, %0, %2;\n\t"
+        "subc.u32 %1, %1, 0;"
+        : "+r"(v0), "+r"(v1) : "r"(k));
+    return pack(v0, v1 + k);
 }
 // any 64-bit v -> [0, p]: v - p if v > p (v = p is left alone: "almost canonical")
-NB_D u64 ff_canon_dev(u32 v0, u32 v1) { return ff_add_meps(v0, v1, ff_gt_p_mask(v0, v1)); }
+NB_D u64 ff_canon_dev(u32 v0, u32 v1)
+{
+    u32 f;                                    // f = carry out of v + (2^32 - 2) = [v1 == 2^32 - 1 and v0 >= 2]
+    asm("add.cc.u32 %0, %1, 0xfffffffe;\n\t"
+        "addc.cc.u32 %0, %2, 0;\n\t"
+        "addc.u32 %0, 0, 0;"
+        : "=&r"(f) : "r"(v0), "r"(v1));
+    return ff_add_keps(v0, v1, f);
+}
 // l + m phi + h0 phi^2 + h1 phi^3 -> [0, p].  With phi^2 = phi - 1 and phi^3 = -1 the value is
 // l + (m + h0) phi - (h0 + h1); the carry c of mu = m + h0 is c phi^2 = c phi - c, and mu + c cannot overflow
 // (c = 1 implies mu <= 2^32 - 2), so it is the 64-bit difference  ((mu + c) : l) - (h0 + h1 + c)  >= -2^33 - 1,
@@ -213,9 +183,9 @@ NB_D u64 ff_reduce_limbs(u32 l, u32 m, u32 h0, u32 h1)
 {
     u32 r0, r1, d0, d1, k;
     asm("add.cc.u32 %1, %6, %7;\n\t"         // mu = m + h0
-        NB_ASM_ADDC("%1", "%1", "%9")          // + c (the flag is left untouched)
+        "addc.u32 %1, %1, 0;\n\t"            // + c (the flag is left untouched)
         "addc.cc.u32 %2, %7, %8;\n\t"        // d = h0 + h1 + c
-        NB_ASM_ADDC("%3", "0", "%9")
+        "addc.u32 %3, 0, 0;\n\t"
         "sub.cc.u32 %0, %5, %2;\n\t"         // (r1 : r0) = (mu + c : l) - d
         "subc.cc.u32 %1, %1, %3;\n\t"
         "subc.u32 %4, 0, 0;\n\t"             // k = -borrow
@@ -223,7 +193,7 @@ NB_D u64 ff_reduce_limbs(u32 l, u32 m, u32 h0, u32 h1)
         "add.cc.u32 %0, %0, %2;\n\t"         // + borrow * p = (k : borrow)
         "addc.u32 %1, %1, %4;"
         : "=&r"(r0), "=&r"(r1), "=&r"(d0), "=&r"(d1), "=&r"(k)
-        : "r"(l), "r"(m), "r"(h0), "r"(h1), "r"(nb_c_zero));
+        : "r"(l), "r"(m), "r"(h0), "r"(h1));
     return ff_canon_dev(r0, r1);
 }
 #endif
@@ -356,21 +326,22 @@ NB_D void mulwide(u32 a, u32 b, u32 &lo, u32 &hi)
     lo = lo32(t); hi = hi32(t);
 }
 // pattern a: (y0 - y2) + (y1 + y2) phi = pack(y0, y1) + y2 * eps.  The product and the 64-bit accumulate are one
-// mad.lo.cc / madc.hi.cc chain (an IMAD.WIDE with carry out).  y2 * eps < 2^63, so the sum is < 2^64 + 2^63: a carry
+// mad.lo.cc / madc.hi.cc chain (carry on the FMA pipe).  y2 * eps < 2^63, so the sum is < 2^64 + 2^63: a carry
 // folds as + eps (no second carry, result < p); without a carry the sum may exceed p.  The two cases exclude each
-// other and share one masked addition of eps.
+// other, so they share one IMAD.WIDE: + (carry | sum > p) * eps.
 NB_D u64 ff_comb_a(u32 y0, u32 y1, u32 y2)
 {
-    u32 r0, r1, k, m;
+    u32 r0, r1, k, f;
     asm("mad.lo.cc.u32 %0, %6, %7, %4;\n\t"
         "madc.hi.cc.u32 %1, %6, %7, %5;\n\t"
-        NB_ASM_ADDC("%2", "0", "%8")           // k = carry
-        "sub.cc.u32 %3, 1, %0;\n\t"          // m = -[sum > p]  (ff_gt_p_mask)
-        "subc.cc.u32 %3, 0xffffffff, %1;\n\t"
-        "subc.u32 %3, 0, 0;"
-        : "=&r"(r0), "=&r"(r1), "=&r"(k), "=&r"(m)
-        : "r"(y0), "r"(y1), "r"(y2), "r"(nb_c_eps), "r"(nb_c_zero));
-    return ff_add_meps(r0, r1, m - k);
+        "addc.u32 %2, 0, 0;\n\t"
+        "add.cc.u32 %3, %0, 0xfffffffe;\n\t"
+        "addc.cc.u32 %3, %1, 0;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(k), "=&r"(f)
+        : "r"(y0), "r"(y1), "r"(y2), "r"(nb_c_eps));
+    (void)f;
+    return ff_add_keps(r0, r1, k);
 }
 // pattern b: (-y1 - y2) + (y0 + y1) phi.  The carry c of s = y0 + y1 is c phi^2 = c phi - c and s + c cannot
 // overflow, so the value is the 64-bit difference ((s + c) : 0) - (y1 + y2 + c) in [-2^33, p - 1]: one borrow
@@ -379,9 +350,9 @@ NB_D u64 ff_comb_b(u32 y0, u32 y1, u32 y2)
 {
     u32 r0, r1, d0, d1, k;
     asm("add.cc.u32 %1, %5, %6;\n\t"         // s = y0 + y1
-        NB_ASM_ADDC("%1", "%1", "%8")          // + c (flag untouched)
+        "addc.u32 %1, %1, 0;\n\t"            // + c (flag untouched)
         "addc.cc.u32 %2, %6, %7;\n\t"        // d = y1 + y2 + c
-        NB_ASM_ADDC("%3", "0", "%8")
+        "addc.u32 %3, 0, 0;\n\t"
         "sub.cc.u32 %0, 0, %2;\n\t"          // (r1 : r0) = ((s + c) : 0) - d
         "subc.cc.u32 %1, %1, %3;\n\t"
         "subc.u32 %4, 0, 0;\n\t"             // k = -borrow
@@ -389,7 +360,7 @@ NB_D u64 ff_comb_b(u32 y0, u32 y1, u32 y2)
         "add.cc.u32 %0, %0, %2;\n\t"         // + borrow * p = (k : borrow)
         "addc.u32 %1, %1, %4;"
         : "=&r"(r0), "=&r"(r1), "=&r"(d0), "=&r"(d1), "=&r"(k)
-        : "r"(y0), "r"(y1), "r"(y2), "r"(nb_c_zero));
+        : "r"(y0), "r"(y1), "r"(y2));
     return pack(r0, r1);
 }
 // pattern c: (-y0 - y1) + (y0 - y2) phi = y0 * eps - pack(y1, y2);  pack(y1, y2) < 2^63
@@ -412,8 +383,6 @@ template <int S> NB_D u64 ff_shl_dev(u64 x)
     u32 y0, y1, y2;
     if (r == 0) { y0 = lo32(x); y1 = hi32(x); y2 = 0; }
     else {
-// plain shifts (SHF / LEA on the ALU pipe, IMAD.SHL on the FMA pipe).  Two IMAD.WIDE by 2^r do the same with one
-        // OR, but IMAD.WIDE issues every 4 cycles: measured slower (profiles/r1b_variants.md)
         y0 = lo32(x) << r;
         y1 = (hi32(x) << r) | (lo32(x) >> (32 - r));
         y2 = hi32(x) >> (32 - r);

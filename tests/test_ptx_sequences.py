@@ -16,15 +16,7 @@ from ptx_emul import Machine, extract_asm_blocks, preprocess, M32, M64
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RAW = open(os.path.join(ROOT, 'nufhe_b200', 'csrc', 'ff.cuh')).read()
 
-
-def _default(name):
-    import re
-    return int(re.search(r'#define %s (\d+)' % name, RAW).group(1))
-
-
-# the build's defaults of the variant knobs (each alternative is also exercised below)
-KNOBS = {k: _default(k) for k in ('NB_FMA_CARRY',)}
-SRC = preprocess(RAW, KNOBS)
+SRC = preprocess(RAW, {})
 P = (1 << 64) - (1 << 32) + 1
 EPS = (1 << 32) - 1
 
@@ -33,7 +25,6 @@ HELPERS = {
     'hi32': lambda x: (x >> 32) & M32,
     'pack': lambda lo, hi: ((hi & M32) << 32) | (lo & M32),
     'nb_c_eps': EPS,
-    'nb_c_zero': 0,
     'nb_c_pow2': [1 << i for i in range(32)],
 }
 _BLOCKS = {}
@@ -59,23 +50,17 @@ def ff_sub(a, b):
 
 
 def ff_add(a, b):
-    if KNOBS['NB_FMA_CARRY']:
-        e = run('ff_add', b=b)
-        return ff_sub(a, HELPERS['pack'](e['n0'], e['n1']))
     return ff_sub(a, (P - b) & M64)
 
 
-def ff_add_meps(v0, v1, m):
-    e = run('ff_add_meps', v0=v0, v1=v1, m=m)
-    return HELPERS['pack'](e['v0'], e['v1'])
-
-
-def ff_gt_p_mask(v0, v1):
-    return run('ff_gt_p_mask', v0=v0, v1=v1)['m']
+def ff_add_keps(v0, v1, k):
+    e = run('ff_add_keps', v0=v0, v1=v1, k=k)
+    return HELPERS['pack'](e['v0'], (e['v1'] + k) & M32)
 
 
 def ff_canon_dev(v0, v1):
-    return ff_add_meps(v0, v1, ff_gt_p_mask(v0, v1))
+    e = run('ff_canon_dev', v0=v0, v1=v1)
+    return ff_add_keps(v0, v1, e['f'])
 
 
 def ff_reduce_limbs(l, m, h0, h1):
@@ -107,7 +92,7 @@ def mulwide(a, b):
 
 def ff_comb_a(y0, y1, y2):
     e = run('ff_comb_a', y0=y0, y1=y1, y2=y2)
-    return ff_add_meps(e['r0'], e['r1'], (e['m'] - e['k']) & M32)
+    return ff_add_keps(e['r0'], e['r1'], e['k'])
 
 
 def ff_comb_b(y0, y1, y2):
@@ -147,22 +132,6 @@ def ff_shl(x, S):
     return ff_shl_dev(x, S)
 
 
-@pytest.fixture(params=[None, {'NB_FMA_CARRY': 0}], autouse=True, ids=['default', 'plain-addc'])
-def knobs(request):
-    """Every test runs with the default knobs and with each alternative code path selected."""
-    global SRC
-    saved = dict(KNOBS)
-    if request.param:
-        KNOBS.update({k: v for k, v in request.param.items()})
-    SRC = preprocess(RAW, KNOBS)
-    _BLOCKS.clear()
-    yield
-    KNOBS.clear()
-    KNOBS.update(saved)
-    SRC = preprocess(RAW, KNOBS)
-    _BLOCKS.clear()
-
-
 # ---- inputs -------------------------------------------------------------------------------------
 EDGE64 = sorted({0, 1, 2, 3, (1 << 31) - 1, 1 << 31, EPS - 1, EPS, EPS + 1, EPS + 2, 1 << 33, (1 << 33) + 1,
                  (1 << 63) - 1, 1 << 63, (1 << 63) + EPS, (1 << 64) - (1 << 33), P - (1 << 33) - 1, P - (1 << 33),
@@ -182,7 +151,7 @@ def in_range(v):
 
 
 def test_parser_sees_every_device_sequence():
-    for fn, n in (('ff_sub', 1), ('mul128', 1), ('mac128', 1), ('ff_add_meps', 1), ('ff_gt_p_mask', 1),
+    for fn, n in (('ff_sub', 1), ('mul128', 1), ('mac128', 1), ('ff_add_keps', 1), ('ff_canon_dev', 1),
                   ('ff_reduce_limbs', 1), ('ff_comb_a', 1), ('ff_comb_b', 1), ('mulwide', 1)):
         assert len(blocks(fn)) == n, fn
 
@@ -210,20 +179,12 @@ def test_sub_add_all_edge_pairs():
         assert ff_add(a, b) % P == (a + b) % P and in_range(ff_add(a, b))
 
 
-def test_canon_and_masked_eps():
+def test_canon_and_keps():
     for v in EDGE64 + LOOSE64 + [RNG.randrange(1 << 64) for _ in range(500)]:
         got = ff_canon_dev(v & M32, v >> 32)
         assert got == (v - P if v > P else v), hex(v)
-        assert ff_gt_p_mask(v & M32, v >> 32) == (M32 if v > P else 0)
         for k in (0, 1):
-            assert ff_add_meps(v & M32, v >> 32, k * M32) == (v + k * EPS) & M64
-
-
-def test_negation_inside_add():
-    for b in EDGE64 + rand_field(500):
-        if KNOBS['NB_FMA_CARRY']:
-            e = run('ff_add', b=b)
-            assert HELPERS['pack'](e['n0'], e['n1']) == P - b, hex(b)
+            assert ff_add_keps(v & M32, v >> 32, k) == (v + k * EPS) & M64
 
 
 def test_reduce_limbs_all_edge_limbs():
