@@ -60,25 +60,46 @@ NB_HD u64 ff_canon(u64 x) { return x >= FF_P ? x - FF_P : x; }
 
 // a - b mod p; a may be any 64-bit value, b canonical; result canonical iff a canonical.
 // (arithmetic.mako:122-161 `sub`): wrap-around of 2^64 is undone by subtracting 2^32-1.
+#if defined(__CUDA_ARCH__)
+#ifndef NB_SUB_CHAIN
+#define NB_SUB_CHAIN 0      // experiment knob: bit 0 = ff_sub, bit 1 = ff_add use the 5-instruction borrow chain
+#endif
+// d = a - b mod 2^64; on a borrow add p.  CHAIN = false: + (m : beta) with beta = borrow, m = -borrow, as an add chain
+// (6 instructions, 3 of them carry producers tied to the ALU pipe, the rest IMAD.X / IMAD.MOV).  CHAIN = true: a
+// second borrow chain, - (0 : m) (5 instructions, 4 on the ALU pipe).
+template <bool CHAIN> NB_D u64 ff_sub_dev(u64 a, u64 b)
+{
+    if constexpr (CHAIN) {
+        u32 l, h, m;
+        asm("sub.cc.u32 %0, %3, %5;\n\t"
+            "subc.cc.u32 %1, %4, %6;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, %2;\n\t"
+            "subc.u32 %1, %1, 0;"
+            : "=&r"(l), "=&r"(h), "=&r"(m)
+            : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+        (void)m;
+        return pack(l, h);
+    } else {
+        u32 l, h, m, be;
+        asm("sub.cc.u32 %0, %4, %6;\n\t"
+            "subc.cc.u32 %1, %5, %7;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "sub.u32 %3, 0, %2;\n\t"
+            "add.cc.u32 %0, %0, %3;\n\t"
+            "addc.u32 %1, %1, %2;"
+            : "=&r"(l), "=&r"(h), "=&r"(m), "=&r"(be)
+            : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+        (void)be;
+        return pack(l, h);
+    }
+}
+#endif
+
 NB_HD u64 ff_sub(u64 a, u64 b)
 {
 #if defined(__CUDA_ARCH__)
-    // d = a - b mod 2^64; on a borrow add p = (m : beta) with beta = borrow, m = -borrow.  Three instructions are
-    // tied to the ALU pipe (the carry producers); m, beta and the last addc compile to IMAD.X / IMAD.MOV on the FMA
-    // pipe.  Measured alternatives (profiles/r1b_variants.md): a second borrow chain (4 ALU instructions, +6 %), and
-    // the fold as ONE IMAD.WIDE with a 64-bit addend (d + m * m, then hi -= m) -- fewest instructions, slowest:
-    // that form issues every 4 cycles and blocks the ALU pipe next to it (+8 %).
-    u32 l, h, m, be;
-    asm("sub.cc.u32 %0, %4, %6;\n\t"
-        "subc.cc.u32 %1, %5, %7;\n\t"
-        "subc.u32 %2, 0, 0;\n\t"
-        "sub.u32 %3, 0, %2;\n\t"
-        "add.cc.u32 %0, %0, %3;\n\t"
-        "addc.u32 %1, %1, %2;"
-        : "=&r"(l), "=&r"(h), "=&r"(m), "=&r"(be)
-        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
-    (void)be;
-    return pack(l, h);
+    return ff_sub_dev<(NB_SUB_CHAIN & 1) != 0>(a, b);
 #else
     u64 d = a - b;
     return a < b ? d - FF_EPS : d;
@@ -88,7 +109,14 @@ NB_HD u64 ff_sub(u64 a, u64 b)
 NB_HD u64 ff_neg(u64 a) { return a ? FF_P - a : 0; }
 
 // a + b mod p, both canonical (arithmetic.mako:78-119 `add`), computed as a - (p - b).
-NB_HD u64 ff_add(u64 a, u64 b) { return ff_sub(a, FF_P - b); }
+NB_HD u64 ff_add(u64 a, u64 b)
+{
+#if defined(__CUDA_ARCH__)
+    return ff_sub_dev<(NB_SUB_CHAIN & 2) != 0>(a, FF_P - b);
+#else
+    return ff_sub(a, FF_P - b);
+#endif
+}
 
 // v * (2^32 - 1) for a 32-bit v: always canonical ((2^32-1)^2 < p).
 NB_HD u64 ff_eps_mul(u32 v)

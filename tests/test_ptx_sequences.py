@@ -44,8 +44,9 @@ def run(fn, index=0, **variables):
 
 
 # ---- mirrors of the C glue ------------------------------------------------------------------------
-def ff_sub(a, b):
-    e = run('ff_sub', a=a, b=b)
+def ff_sub(a, b, chain=False):
+    # ff_sub_dev<CHAIN>: block 0 = second borrow chain, block 1 = add-chain fold (the one the build uses)
+    e = run('ff_sub_dev', 0 if chain else 1, a=a, b=b)
     return HELPERS['pack'](e['l'], e['h'])
 
 
@@ -151,7 +152,7 @@ def in_range(v):
 
 
 def test_parser_sees_every_device_sequence():
-    for fn, n in (('ff_sub', 1), ('mul128', 1), ('mac128', 1), ('ff_add_keps', 1), ('ff_canon_dev', 1),
+    for fn, n in (('ff_sub_dev', 2), ('mul128', 1), ('mac128', 1), ('ff_add_keps', 1), ('ff_canon_dev', 1),
                   ('ff_reduce_limbs', 1), ('ff_comb_a', 1), ('ff_comb_b', 1), ('mulwide', 1)):
         assert len(blocks(fn)) == n, fn
 
@@ -163,13 +164,14 @@ def test_carry_flag_families_are_never_mixed():
 
 
 def test_sub_add_all_edge_pairs():
-    for a in EDGE64 + LOOSE64:
-        for b in EDGE64:
-            got = ff_sub(a, b)
-            want = a - b if a >= b else a - b + P          # exact, no further reduction (a may be loose)
-            assert got == want, (hex(a), hex(b), hex(got), hex(want))
-            if a <= P:
-                assert in_range(got)
+    for chain in (False, True):
+        for a in EDGE64 + LOOSE64:
+            for b in EDGE64:
+                got = ff_sub(a, b, chain)
+                want = a - b if a >= b else a - b + P          # exact, no further reduction (a may be loose)
+                assert got == want, (chain, hex(a), hex(b), hex(got), hex(want))
+                if a <= P:
+                    assert in_range(got)
     for a in EDGE64:
         for b in EDGE64:
             got = ff_add(a, b)

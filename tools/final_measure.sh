@@ -1,12 +1,7 @@
-# Round-end measurement on one B200: variant A/B, GPU tests, bench lines, sweep, ncu launch list + full capture.
+# Round-end measurement on one B200: GPU tests, bench lines, sweep, ncu launch list + full capture.
 set -x
 O=gpurun_out/fin
 mkdir -p $O
-for v in tools/variants/*.so; do
-  n=$(basename $v .so)
-  NUFHE_B200_LIB=$PWD/$v timeout 300 python tools/profile_target.py 4096 16384 > $O/var_$n.txt 2>&1
-done
-grep -H "TIMES\|checksum" $O/var_*.txt
 timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3 > $O/pytest.txt
 python bench.py --steps 5 --warmup 3 > $O/bench_nand.json 2> $O/bench_nand.err
 python bench.py --steps 5 --warmup 3 --gate mux > $O/bench_mux.json 2> $O/bench_mux.err
@@ -16,4 +11,3 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"blind_rotate|keyswitch_kernel|ntt_forward|ntt_inverse" -c 4 -o $O/r1b_fin python tools/profile_target.py 592 16384 > $O/prof.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.txt 2>&1
 cat $O/pytest.txt $O/bench_nand.json $O/bench_mux.json $O/bench_ref.json $O/smoke.txt
-grep -H "TIMES\|checksum" $O/var_*.txt
