@@ -103,6 +103,31 @@ int nb_lwe_affine(nb_ctx *ctx, int32_t *res_a, int32_t *res_b, const int32_t *x1
                   const int32_t *x2_a, const int32_t *x2_b, int32_t c, int32_t s1, int32_t s2, size_t batch,
                   size_t n);
 
+/* ---- the separate steps of the multi-kernel bootstrap (bootstrap.py:96-196), `single_kernel_bootstrap=False` ---- */
+/* ShiftTorusPolynomial (polynomials.py:90-104, polynomials_gpu.mako:18-77).  mode NB_SHIFT_INVERT: result =
+ * X^(2N - power) * source (shift_tp_inverted_power); NB_SHIFT_MINUS_ONE: (X^power - 1) * source
+ * (shift_tp_minus_one_power_from_array / tlwe_shift_polynomials); NB_SHIFT_PLAIN: X^power * source.
+ * source/result: (polys, N) int32, N = 2^n_log2.  Polynomial p uses
+ * powers[(p / polys_per_power) * powers_stride + power_idx]. */
+#define NB_SHIFT_INVERT 0
+#define NB_SHIFT_MINUS_ONE 1
+#define NB_SHIFT_PLAIN 2
+int nb_shift_torus_polynomial(nb_ctx *ctx, int32_t *result, const int32_t *source, const int32_t *powers,
+                              size_t powers_stride, size_t power_idx, int polys_per_power, int mode, int n_log2,
+                              size_t polys);
+/* tlwe_noiseless_trivial (tlwe.py:156-158): acc (B, k+1, N) = (0, .., 0, mu (B, N)); cv (B, k+1) = 0 (may be NULL) */
+int nb_tlwe_noiseless_trivial(nb_ctx *ctx, int32_t *acc, float *cv, const int32_t *mu, int mask_size, int n_log2,
+                              size_t batch);
+/* tlwe_extract_lwe_samples (tlwe.py:161-165): out_a (B, k*N), out_b (B,) from acc (B, k+1, N) */
+int nb_tlwe_extract_lwe_samples(nb_ctx *ctx, int32_t *out_a, int32_t *out_b, const int32_t *acc, int mask_size,
+                                int n_log2, size_t batch);
+/* t32_to_phase (numeric_functions.py:34-36, kernel numeric_functions_gpu.py:39-77): the mod-switch of bootstrap()
+ * (bootstrap.py:216-219) as a separate step; mspace_size must divide 2^32 */
+int nb_t32_to_phase(nb_ctx *ctx, int32_t *out, const int32_t *in, size_t n, uint32_t mspace_size);
+/* tlwe_add_to (tlwe.py:173-175): res += src (int32 wrap-around, n elements); variances (n_cv floats, may be NULL) */
+int nb_tlwe_add_to(nb_ctx *ctx, int32_t *res, const int32_t *src, size_t n, float *res_cv, const float *src_cv,
+                   size_t n_cv);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,11 @@ SIGNATURES = {
                               _vp, _sz, _vp, _vp, _sz],
     'nb_keyswitch': [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _sz, _int, _int, _vp, _vp, _vp, _sz],
     'nb_lwe_affine': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _sz, _sz],
+    'nb_shift_torus_polynomial': [_vp, _vp, _vp, _vp, _sz, _sz, _int, _int, _int, _sz],
+    'nb_tlwe_noiseless_trivial': [_vp, _vp, _vp, _vp, _int, _int, _sz],
+    'nb_tlwe_extract_lwe_samples': [_vp, _vp, _vp, _vp, _int, _int, _sz],
+    'nb_tlwe_add_to': [_vp, _vp, _vp, _sz, _vp, _vp, _sz],
+    'nb_t32_to_phase': [_vp, _vp, _vp, _sz, ctypes.c_uint32],
 }
 _RESTYPES = {'nb_bk_row_u64': ctypes.c_size_t, 'nb_ctx_destroy': None, 'nb_last_error': ctypes.c_char_p, 'nb_build_info': ctypes.c_char_p}
 

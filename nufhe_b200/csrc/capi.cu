@@ -304,6 +304,78 @@ int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, cons
     return launch_check(ctx, "keyswitch_kernel");
 }
 
+static int ew_grid(nb_ctx *ctx, size_t n)
+{
+    size_t blocks = (n + 255) / 256, cap = (size_t)ctx->sm_count * 16;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+int nb_shift_torus_polynomial(nb_ctx *ctx, int32_t *result, const int32_t *source, const int32_t *powers,
+                              size_t powers_stride, size_t power_idx, int polys_per_power, int mode, int n_log2,
+                              size_t polys)
+{
+    if (!ctx) return NB_EINVAL;
+    if (!result || !source || !powers) return fail(ctx, NB_EINVAL, "nb_shift_torus_polynomial: null argument");
+    if (mode < NB_SHIFT_INVERT || mode > NB_SHIFT_PLAIN) return fail(ctx, NB_EINVAL, "nb_shift_torus_polynomial: unknown mode");
+    if (n_log2 < 1 || n_log2 > 20 || polys_per_power < 1) return fail(ctx, NB_EINVAL, "nb_shift_torus_polynomial: bad size");
+    if (result == source) return fail(ctx, NB_EINVAL, "nb_shift_torus_polynomial: result must not alias source");
+    if (polys == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    shift_torus_polynomial_kernel<<<ew_grid(ctx, polys << n_log2), 256, 0, ctx->stream>>>(
+        result, source, powers, powers_stride, power_idx, polys_per_power, mode, n_log2, polys);
+    return launch_check(ctx, "shift_torus_polynomial_kernel");
+}
+
+int nb_tlwe_noiseless_trivial(nb_ctx *ctx, int32_t *acc, float *cv, const int32_t *mu, int mask_size, int n_log2,
+                              size_t batch)
+{
+    if (!ctx) return NB_EINVAL;
+    if (!acc || !mu) return fail(ctx, NB_EINVAL, "nb_tlwe_noiseless_trivial: null argument");
+    if (mask_size < 1 || n_log2 < 1 || n_log2 > 20) return fail(ctx, NB_EINVAL, "nb_tlwe_noiseless_trivial: bad size");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    tlwe_noiseless_trivial_kernel<<<ew_grid(ctx, (batch * (mask_size + 1)) << n_log2), 256, 0, ctx->stream>>>(
+        acc, cv, mu, mask_size, n_log2, batch);
+    return launch_check(ctx, "tlwe_noiseless_trivial_kernel");
+}
+
+int nb_tlwe_extract_lwe_samples(nb_ctx *ctx, int32_t *out_a, int32_t *out_b, const int32_t *acc, int mask_size,
+                                int n_log2, size_t batch)
+{
+    if (!ctx) return NB_EINVAL;
+    if (!out_a || !out_b || !acc) return fail(ctx, NB_EINVAL, "nb_tlwe_extract_lwe_samples: null argument");
+    if (mask_size < 1 || n_log2 < 1 || n_log2 > 20) return fail(ctx, NB_EINVAL, "nb_tlwe_extract_lwe_samples: bad size");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    tlwe_extract_lwe_samples_kernel<<<ew_grid(ctx, (batch * mask_size) << n_log2), 256, 0, ctx->stream>>>(
+        out_a, out_b, acc, mask_size, n_log2, batch);
+    return launch_check(ctx, "tlwe_extract_lwe_samples_kernel");
+}
+
+int nb_t32_to_phase(nb_ctx *ctx, int32_t *out, const int32_t *in, size_t n, uint32_t mspace_size)
+{
+    if (!ctx) return NB_EINVAL;
+    if (!out || !in) return fail(ctx, NB_EINVAL, "nb_t32_to_phase: null argument");
+    if (mspace_size == 0 || (mspace_size & (mspace_size - 1))) return fail(ctx, NB_EINVAL, "nb_t32_to_phase: mspace_size must be a power of two");
+    if (n == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    t32_to_phase_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(out, in, n, mspace_size);
+    return launch_check(ctx, "t32_to_phase_kernel");
+}
+
+int nb_tlwe_add_to(nb_ctx *ctx, int32_t *res, const int32_t *src, size_t n, float *res_cv, const float *src_cv,
+                   size_t n_cv)
+{
+    if (!ctx) return NB_EINVAL;
+    if (!res || !src || ((res_cv == nullptr) != (src_cv == nullptr)))
+        return fail(ctx, NB_EINVAL, "nb_tlwe_add_to: null argument");
+    if (n_cv > n) return fail(ctx, NB_EINVAL, "nb_tlwe_add_to: more variances than coefficients");
+    if (n == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    add_to_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(res, src, n, res_cv, src_cv, res_cv ? n_cv : 0);
+    return launch_check(ctx, "add_to_kernel");
+}
+
 int nb_lwe_affine(nb_ctx *ctx, int32_t *res_a, int32_t *res_b, const int32_t *x1_a, const int32_t *x1_b,
                   const int32_t *x2_a, const int32_t *x2_b, int32_t c, int32_t s1, int32_t s2, size_t batch,
                   size_t n)

@@ -327,6 +327,85 @@ __global__ void __launch_bounds__(BR2_THREADS, BR2_CTAS_PER_SM) blind_rotate_ker
     }
 }
 
+// ---- the separate kernels of the reference's multi-kernel bootstrap (bootstrap.py:96-196) ---------------
+// They exist so that `single_kernel_bootstrap=False` and callers of the inner seams get the same
+// functions with the same results; the fused kernel above does all of this in shared memory.
+//
+// ShiftTorusPolynomial (polynomials_gpu.mako:18-77; polynomials_cpu.py:25-59): result = X^e * source with
+// e = power (mode 2), 2N - power (mode 0, `invert_powers`), or result = (X^power - 1) * source (mode 1,
+// `minus_one`).  One power per group of `polys_per_power` consecutive polynomials, read from
+// powers[group * powers_stride + power_idx] (the reference's `powers_view`).
+__global__ void shift_torus_polynomial_kernel(i32 *__restrict__ result, const i32 *__restrict__ source,
+                                              const i32 *__restrict__ powers, size_t powers_stride, size_t power_idx,
+                                              int polys_per_power, int mode, int n_log2, size_t polys)
+{
+    const int N = 1 << n_log2;
+    const size_t total = polys << n_log2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = i >> n_log2;
+        const int idx = (int)(i & (N - 1));
+        int pw = powers[(poly / polys_per_power) * powers_stride + power_idx];
+        if (mode == 0) pw = 2 * N - pw;
+        pw &= 2 * N - 1;
+        const int ar = pw & (N - 1);
+        const bool flip = pw >= N;
+        const i32 src = source[poly * N + ((idx - ar) & (N - 1))];
+        const bool neg = (idx < ar) != flip;
+        u32 v = neg ? 0u - (u32)src : (u32)src;
+        if (mode == 1) v -= (u32)source[poly * N + idx];
+        result[i] = (i32)v;
+    }
+}
+
+// TLweNoiselessTrivial (tlwe_gpu.py:32-74; tlwe_cpu.py:26-38): acc = (0, ..., 0, mu), variances 0
+__global__ void tlwe_noiseless_trivial_kernel(i32 *__restrict__ acc, float *__restrict__ cv, const i32 *__restrict__ mu,
+                                              int mask_size, int n_log2, size_t batch)
+{
+    const int N = 1 << n_log2;
+    const size_t per = (size_t)(mask_size + 1) << n_log2, total = batch * per;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / per, r = i % per;
+        const int poly = (int)(r >> n_log2), x = (int)(r & (N - 1));
+        acc[i] = poly == mask_size ? mu[c * N + x] : 0;
+        if (cv && i < batch * (size_t)(mask_size + 1)) cv[i] = 0.f;
+    }
+}
+
+// TLweExtractLweSamples (tlwe_gpu.mako:54-84; tlwe_cpu.py:41-60): a[i*N] = acc_i[0], a[i*N + x] = -acc_i[N - x],
+// b = acc_k[0]
+__global__ void tlwe_extract_lwe_samples_kernel(i32 *__restrict__ out_a, i32 *__restrict__ out_b,
+                                                const i32 *__restrict__ acc, int mask_size, int n_log2, size_t batch)
+{
+    const int N = 1 << n_log2;
+    const size_t per = (size_t)mask_size << n_log2, total = batch * per;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / per, r = i % per;
+        const int poly = (int)(r >> n_log2), x = (int)(r & (N - 1));
+        const i32 *a = acc + ((c * (mask_size + 1) + poly) << n_log2);
+        out_a[i] = x == 0 ? a[0] : (i32)(0u - (u32)a[N - x]);
+        if (r == 0) out_b[c] = acc[(c * (mask_size + 1) + mask_size) << n_log2];
+    }
+}
+
+// Torus32ToPhase (numeric_functions_gpu.py:39-77; numeric_functions_cpu.py:23-37): round to a multiple of
+// 2^32 / mspace_size and return the multiple, in [0, mspace_size)
+__global__ void t32_to_phase_kernel(i32 *__restrict__ out, const i32 *__restrict__ in, size_t n, u32 mspace_size)
+{
+    const u32 interv = (u32)((1ull << 32) / mspace_size), half = interv / 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (i32)(((u32)in[i] + half) / interv);
+}
+
+// tlwe_add_to (tlwe.py:173-175): wrap-around int32 addition, float addition of the variances
+__global__ void add_to_kernel(i32 *__restrict__ res, const i32 *__restrict__ src, size_t n, float *__restrict__ res_cv,
+                              const float *__restrict__ src_cv, size_t n_cv)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        res[i] = (i32)((u32)res[i] + (u32)src[i]);
+        if (res_cv && i < n_cv) res_cv[i] += src_cv[i];
+    }
+}
+
 // ---- LWE key switch (lwe_gpu.mako:59-118; lwe_cpu.py:62-93) --------------------------------------
 // res_a[i] = - sum_{j,k} ks_a[j][k][digit(j,k)][i], res_b = b - sum ks_b[j][k][digit].
 //

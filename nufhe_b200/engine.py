@@ -193,6 +193,53 @@ class Engine:
                    _ptr(res_cv), B)
         return res_a, res_b, res_cv
 
+    # --- the separate steps of the multi-kernel bootstrap (bootstrap.py:96-196) -------------------
+    SHIFT_INVERT, SHIFT_MINUS_ONE, SHIFT_PLAIN = 0, 1, 2
+
+    def shift_torus_polynomial(self, result, source, powers, power_idx=0, polys_per_power=1, mode=0):
+        """result (polys, N) <- X^e * source; one power per `polys_per_power` polynomials, column `power_idx` of
+        `powers` (rows of `powers.shape[-1]` entries when it is 2-D per group, else one entry per group)."""
+        assert result.is_contiguous() and result.dtype == torch.int32
+        source = self._dense(source, torch.int32)
+        powers = self._dense(powers, torch.int32)
+        n_poly = result.shape[-1]
+        polys = result.numel() // n_poly
+        groups = polys // polys_per_power
+        stride = powers.numel() // groups
+        self._call('nb_shift_torus_polynomial', _ptr(result), _ptr(source), _ptr(powers), stride, power_idx,
+                   polys_per_power, mode, n_poly.bit_length() - 1, polys)
+        return result
+
+    def tlwe_noiseless_trivial(self, acc, cv, mu):
+        assert acc.is_contiguous() and acc.dtype == torch.int32
+        mu = self._dense(mu, torch.int32)
+        n_poly, k1 = acc.shape[-1], acc.shape[-2]
+        self._call('nb_tlwe_noiseless_trivial', _ptr(acc), _ptr(cv), _ptr(mu), k1 - 1, n_poly.bit_length() - 1,
+                   acc.numel() // (k1 * n_poly))
+        return acc
+
+    def tlwe_extract_lwe_samples(self, out_a, out_b, acc):
+        assert out_a.is_contiguous() and out_b.is_contiguous()
+        acc = self._dense(acc, torch.int32)
+        n_poly, k1 = acc.shape[-1], acc.shape[-2]
+        self._call('nb_tlwe_extract_lwe_samples', _ptr(out_a), _ptr(out_b), _ptr(acc), k1 - 1,
+                   n_poly.bit_length() - 1, acc.numel() // (k1 * n_poly))
+
+    def tlwe_add_to(self, res, src, res_cv=None, src_cv=None):
+        assert res.is_contiguous() and res.dtype == torch.int32
+        src = self._dense(src, torch.int32)
+        if res_cv is not None:
+            assert res_cv.is_contiguous()
+            src_cv = self._dense(src_cv, torch.float32)
+        self._call('nb_tlwe_add_to', _ptr(res), _ptr(src), res.numel(), _ptr(res_cv), _ptr(src_cv),
+                   0 if res_cv is None else res_cv.numel())
+
+    def t32_to_phase(self, out, messages, mspace_size):
+        assert out.is_contiguous() and out.dtype == torch.int32
+        messages = self._dense(messages, torch.int32)
+        self._call('nb_t32_to_phase', _ptr(out), _ptr(messages), out.numel(), int(mspace_size))
+        return out
+
     def lwe_affine(self, res, x1, x2, c, s1, s2):
         res_a, res_b = res
         B = res_b.numel()

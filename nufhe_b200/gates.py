@@ -7,8 +7,9 @@ import numpy
 
 from .numeric_functions import phase_to_t32
 from .lwe import (
-    LweSampleArray, lwe_negate, lwe_copy, lwe_noiseless_trivial, _keyswitch_into)
-from .bootstrap import bootstrap_affine
+    LweSampleArray, lwe_negate, lwe_copy, lwe_noiseless_trivial, lwe_noiseless_trivial_constant, lwe_add_mul_to,
+    lwe_add_to, lwe_sub_to, lwe_keyswitch, _keyswitch_into)
+from .bootstrap import bootstrap_affine, bootstrap, _single_kernel
 from .tgsw import engine_format
 from .performance import PerformanceParameters, PerformanceParametersForDevice
 
@@ -71,6 +72,15 @@ _BINARY_GATES = {
 def _binary_gate(name, thr, cloud_key, result, a, b, perf_params):
     check_shape(result, a, b)
     num, den, sa, sb = _BINARY_GATES[name]
+    if not _single_kernel(perf_params):
+        # the reference's own sequence (gates.py:108-121): trivial constant, two linear updates, bootstrap
+        bk = cloud_key.bootstrap_key
+        temp = LweSampleArray.empty(thr, bk.in_out_params, result.shape)
+        lwe_noiseless_trivial_constant(thr, temp, phase_to_t32(num, den))
+        lwe_add_mul_to(thr, temp, sa, a)
+        lwe_add_mul_to(thr, temp, sb, b)
+        bootstrap(thr, result, bk, cloud_key.keyswitch_key, MU, temp, perf_params)
+        return
     bootstrap_affine(
         thr, result, cloud_key.bootstrap_key, cloud_key.keyswitch_key, MU,
         a, b, phase_to_t32(num, den), sa, sb)
@@ -140,6 +150,26 @@ def gate_mux(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, b: LweSa
     bk, ks = cloud_key.bootstrap_key, cloud_key.keyswitch_key
     and_const = phase_to_t32(-1, 8)
     shape = tuple(result.shape)
+    if not _single_kernel(perf_params):
+        # the reference's own sequence (gates.py:629-664)
+        in_out, extracted = bk.in_out_params, bk.extract_params
+        temp = LweSampleArray.empty(thr, in_out, shape)
+        temp1 = LweSampleArray.empty(thr, extracted, shape)
+        u1 = LweSampleArray.empty(thr, extracted, shape)
+        u2 = LweSampleArray.empty(thr, extracted, shape)
+        lwe_noiseless_trivial_constant(thr, temp, and_const)       # AND(a, b), no key switch
+        lwe_add_to(thr, temp, a)
+        lwe_add_to(thr, temp, b)
+        bootstrap(thr, u1, bk, ks, MU, temp, perf_params, no_keyswitch=True)
+        lwe_noiseless_trivial_constant(thr, temp, and_const)       # AND(not a, c), no key switch
+        lwe_sub_to(thr, temp, a)
+        lwe_add_to(thr, temp, c)
+        bootstrap(thr, u2, bk, ks, MU, temp, perf_params, no_keyswitch=True)
+        lwe_noiseless_trivial_constant(thr, temp1, phase_to_t32(1, 8))
+        lwe_add_to(thr, temp1, u1)
+        lwe_add_to(thr, temp1, u2)
+        lwe_keyswitch(thr, result, ks, temp1)
+        return
 
     def expand(x):
         a, b = x.a, x.b

@@ -24,8 +24,11 @@ def double_to_t32(d):
 
 def t32_to_phase(thr, result, messages, mspace_size: int):
     """Mod-switch (numeric_functions.py:34-36; kernel numeric_functions_gpu.py:39-77).
-    On the gate path this is fused into the bootstrap kernel; this element-wise form exists for
-    API parity and uses torch integer ops on the device."""
-    interv = 2**32 // mspace_size
-    u = messages.to(torch.int64) & 0xffffffff
-    result.copy_((((u + interv // 2) & 0xffffffff) // interv).to(torch.int32))
+    On the single-kernel gate path this is fused into the bootstrap kernel; this is the separate step of the
+    multi-kernel path (nb_t32_to_phase)."""
+    if result.is_contiguous():
+        thr.t32_to_phase(result, messages, mspace_size)
+    else:
+        tmp = torch.empty(tuple(result.shape), dtype=torch.int32, device=result.device)
+        thr.t32_to_phase(tmp, messages, mspace_size)
+        result.copy_(tmp)

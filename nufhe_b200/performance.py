@@ -44,8 +44,8 @@ class PerformanceParameters:
 
 
 class PerformanceParametersForDevice:
-    """performance.py:137-236.  single_kernel_bootstrap is always True here: the fused kernel is the
-    only bootstrap path (the reference's multi-kernel loop exists for OpenCL / k != 1)."""
+    """performance.py:137-236.  `single_kernel_bootstrap` defaults to True (the fused kernel); False selects the
+    reference's multi-kernel sequence of separate launches (bootstrap.py:96-196), same results, much slower."""
 
     def __init__(self, perf_params: PerformanceParameters, device_params):
         self.nufhe_params = perf_params.nufhe_params
@@ -55,11 +55,11 @@ class PerformanceParametersForDevice:
         self.use_constant_memory_multi_iter = False
         self.use_constant_memory_single_iter = False
         self.transforms_per_block = 4
-        self.single_kernel_bootstrap = True
+        self.single_kernel_bootstrap = perf_params.single_kernel_bootstrap is not False
         self.low_end_device = False
 
     def _key(self):
-        return (self.nufhe_params,)
+        return (self.nufhe_params, self.single_kernel_bootstrap)
 
     def __hash__(self):
         return hash((self.__class__,) + self._key())

@@ -55,3 +55,16 @@ class TransformedPolynomialArray:
         return (self.__class__ == other.__class__ and self.transform_type == other.transform_type
                 and self.polynomial_degree == other.polynomial_degree
                 and arrays_equal(self.coeffs, other.coeffs))
+
+
+def shift_tp_inverted_power(thr, result: TorusPolynomialArray, powers, source: TorusPolynomialArray):
+    """result = X^(2N - pwr) * source, one power per polynomial (polynomials.py:90-95, K7 invert_powers)."""
+    thr.shift_torus_polynomial(result.coeffs, source.coeffs, powers, mode=thr.SHIFT_INVERT)
+
+
+def shift_tp_minus_one_power_from_array(thr, result: TorusPolynomialArray, powers, power_idx: int,
+                                        source: TorusPolynomialArray):
+    """result = (X^pwr - 1) * source with pwr = powers[..., power_idx], shared by the polynomials of one sample
+    (polynomials.py:98-104, K7 powers_view + minus_one)."""
+    thr.shift_torus_polynomial(result.coeffs, source.coeffs, powers, power_idx=power_idx,
+                               polys_per_power=result.coeffs.shape[-2], mode=thr.SHIFT_MINUS_ONE)

@@ -125,3 +125,36 @@ def tlwe_transform_samples(thr, result: TransformedTLweSampleArray, source: TLwe
     tr = thr.ntt_forward_i32(source.a.coeffs)
     result.a.coeffs.copy_(thr.ff_op(_native.FF_PREPARE, tr))
     result.current_variances.copy_(source.current_variances)
+
+
+def tlwe_noiseless_trivial(thr, result: TLweSampleArray, mu: TorusPolynomialArray):
+    """result = (0, mu) (tlwe.py:156-158, K8)."""
+    thr.tlwe_noiseless_trivial(result.a.coeffs, result.current_variances, mu.coeffs)
+
+
+def tlwe_extract_lwe_samples(thr, result, x: TLweSampleArray):
+    """Sample extraction (tlwe.py:161-165, K9); `current_variances` of the result is left alone like the reference."""
+    if result.a.is_contiguous() and result.b.is_contiguous():
+        thr.tlwe_extract_lwe_samples(result.a, result.b, x.a.coeffs)
+    else:
+        a, b = torch.empty_like(result.a, memory_format=torch.contiguous_format), torch.empty_like(
+            result.b, memory_format=torch.contiguous_format)
+        thr.tlwe_extract_lwe_samples(a, b, x.a.coeffs)
+        result.a.copy_(a)
+        result.b.copy_(b)
+
+
+def tlwe_shift_polynomials(thr, result: TLweSampleArray, bk: TLweSampleArray, powers, powers_idx):
+    """result = (X^powers[.., powers_idx] - 1) * bk (tlwe.py:168-169)."""
+    from .polynomials import shift_tp_minus_one_power_from_array
+    shift_tp_minus_one_power_from_array(thr, result.a, powers, powers_idx, bk.a)
+
+
+def tlwe_add_to(thr, result: TLweSampleArray, source: TLweSampleArray):
+    """result += source (tlwe.py:173-175)."""
+    thr.tlwe_add_to(result.a.coeffs, source.a.coeffs, result.current_variances, source.current_variances)
+
+
+def tlwe_copy(thr, result: TLweSampleArray, source: TLweSampleArray):
+    """result = source (tlwe.py:178-180; coefficients only, like the reference)."""
+    result.a.coeffs.copy_(source.a.coeffs)

@@ -201,6 +201,55 @@ def test_uint_min_circuit(ctx, key_pair):
     assert (got == numpy.minimum(xs, ys)).all()
 
 
+def test_multi_kernel_bootstrap_equals_fused(ctx, key_pair, nufhe):
+    """`single_kernel_bootstrap=False` runs the reference's literal sequence of separate launches
+    (bootstrap.py:96-229, gates.py:108-121, :629-664); the ciphertexts must equal the fused kernel's bit for bit."""
+    sk, ck = key_pair
+    rng = numpy.random.RandomState(5)
+    bits = [rng.randint(0, 2, size=3).astype(bool) for _ in range(3)]
+    cts = [ctx.encrypt(sk, b) for b in bits]
+    vm1 = ctx.make_virtual_machine(ck)
+    vm2 = ctx.make_virtual_machine(ck, perf_params=nufhe.PerformanceParameters(ck.params, single_kernel_bootstrap=False))
+    assert vm1.perf_params.single_kernel_bootstrap and not vm2.perf_params.single_kernel_bootstrap
+    for name, n_args in (('gate_nand', 2), ('gate_xor', 2), ('gate_mux', 3)):
+        r1 = getattr(vm1, name)(*cts[:n_args])
+        r2 = getattr(vm2, name)(*cts[:n_args])
+        assert (host(r1.a) == host(r2.a)).all() and (host(r1.b) == host(r2.b)).all(), name
+        assert numpy.allclose(host(r1.current_variances), host(r2.current_variances))
+    assert (ctx.decrypt(sk, vm2.gate_nand(cts[0], cts[1])) == ~(bits[0] & bits[1])).all()
+
+
+def test_bootstrap_seams(ctx, key_pair, okeys, nufhe):
+    """The inner seams a caller of the reference can hook: bootstrap(), blind_rotate_and_extract(),
+    blind_rotate(), mux_rotate() -- multi-kernel and fused give the oracle's bits."""
+    from nufhe_b200.bootstrap import bootstrap, blind_rotate, mux_rotate
+    from nufhe_b200.tlwe import TLweSampleArray
+    from nufhe_b200.lwe import LweSampleArray
+    thr = ctx.thread
+    sk, ck = key_pair
+    bk, ks = ck.bootstrap_key, ck.keyswitch_key
+    x = ctx.encrypt(sk, numpy.array([True, False]))
+    want = O.bootstrap(host(x.a), host(x.b), okeys.bk, okeys.ks)
+    pp = nufhe.PerformanceParameters(ck.params, single_kernel_bootstrap=False).for_device(thr.device_params)
+    for perf in (None, pp):
+        res = LweSampleArray.empty(thr, ck.params.in_out_params, (2,))
+        bootstrap(thr, res, bk, ks, O.MU, x, perf)
+        assert (host(res.a) == want[0]).all() and (host(res.b) == want[1]).all()
+    # one CMux step and a 3-row rotation against the oracle
+    rng = G.rs(77)
+    acc0 = G.torus32(rng, (2, 2, 1024))
+    bara = G.torus32(rng, (2, 500), 0, 2048)
+    accum = TLweSampleArray.empty(thr, bk.bk_params.tlwe_params, (2,))
+    accum.a.coeffs.copy_(thr.to_device(acc0))
+    result = TLweSampleArray.empty(thr, bk.bk_params.tlwe_params, (2,))
+    mux_rotate(thr, result, accum, bk.tgsw, 4, thr.to_device(bara))
+    one = O.shift_torus_polynomial(acc0, bara, 4, minus_one=True)
+    one = (O.tgsw_external_mul(one, okeys.bk, 4).view(numpy.uint32) + acc0.view(numpy.uint32)).view(numpy.int32)
+    assert (host(result.a.coeffs) == one).all()
+    blind_rotate(thr, accum, bk, thr.to_device(bara), 3)
+    assert (host(accum.a.coeffs) == O.blind_rotate(acc0, okeys.bk[:3], numpy.ascontiguousarray(bara[:, :3]))).all()
+
+
 def test_find_devices(nufhe):
     devs = nufhe.find_devices()
     assert len(devs) >= 1 and devs[0].api_name == 'CUDA'

@@ -180,3 +180,60 @@ def test_lwe_affine(eng, golden):
         eng.lwe_affine(res, da, db, O.phase_to_t32(num, den), sa, sb)
         assert (eng.to_host(res[0]) == g['lin_%s_a' % name]).all()
         assert (eng.to_host(res[1]) == g['lin_%s_b' % name]).all()
+
+
+def test_multi_kernel_steps_golden(eng, golden):
+    """The separate steps of the reference's multi-kernel bootstrap (bootstrap.py:96-196): mod-switch, the three
+    polynomial rotation modes, trivial sample, sample extraction, accumulator addition -- against the reference's
+    own closures (goldens) and the oracle."""
+    g = golden('small')
+    x = G.modswitch_inputs()
+    out = eng.t32_to_phase(eng.empty(x.shape, torch.int32), eng.to_device(x), 2048)
+    assert (eng.to_host(out) == g['phase']).all()
+    src, powers, bara = G.shift_inputs()
+    dsrc = eng.to_device(src)
+    for mode, key in ((eng.SHIFT_PLAIN, 'shift_plain'), (eng.SHIFT_INVERT, 'shift_inverted')):
+        res = eng.shift_torus_polynomial(torch.empty_like(dsrc), dsrc, eng.to_device(powers), polys_per_power=2, mode=mode)
+        assert (eng.to_host(res) == g[key]).all(), key
+    res = eng.shift_torus_polynomial(torch.empty_like(dsrc), dsrc, eng.to_device(bara), power_idx=3, polys_per_power=2,
+                                     mode=eng.SHIFT_MINUS_ONE)
+    assert (eng.to_host(res) == g['shift_minus_one']).all()
+    acc = eng.to_device(G.extract_inputs())
+    ea, eb = eng.empty((4, 1024), torch.int32), eng.empty((4,), torch.int32)
+    eng.tlwe_extract_lwe_samples(ea, eb, acc)
+    assert (eng.to_host(ea) == g['extract_a']).all() and (eng.to_host(eb) == g['extract_b']).all()
+    triv = eng.empty((9, 2, 1024), torch.int32)
+    cv = torch.full((9,), 3.0, dtype=torch.float32, device=triv.device)
+    eng.tlwe_noiseless_trivial(triv, cv, eng.to_device(numpy.ascontiguousarray(src[:, 0, :])))
+    assert (eng.to_host(triv) == g['trivial']).all() and (eng.to_host(cv) == 0).all()
+
+
+@pytest.mark.parametrize('batch', [1, 33])
+def test_multi_kernel_steps_vs_oracle(eng, batch):
+    rng = G.rs(300 + batch)
+    src = G.torus32(rng, (batch, 2, 1024))
+    bara = G.torus32(rng, (batch, 7), 0, 2048)
+    dsrc = eng.to_device(src)
+    for idx in (0, 6):
+        res = eng.shift_torus_polynomial(torch.empty_like(dsrc), dsrc, eng.to_device(bara), power_idx=idx,
+                                         polys_per_power=2, mode=eng.SHIFT_MINUS_ONE)
+        assert (eng.to_host(res) == O.shift_torus_polynomial(src, bara, idx, minus_one=True)).all()
+    one = numpy.ascontiguousarray(src[:, :1, :])
+    pw = numpy.ascontiguousarray(bara[:, 0])
+    res = eng.shift_torus_polynomial(eng.empty(one.shape, torch.int32), eng.to_device(one), eng.to_device(pw),
+                                     mode=eng.SHIFT_INVERT)
+    assert (eng.to_host(res) == O.shift_torus_polynomial(one, pw, invert_powers=True)).all()
+    ea, eb = eng.empty((batch, 1024), torch.int32), eng.empty((batch,), torch.int32)
+    eng.tlwe_extract_lwe_samples(ea, eb, dsrc)
+    oa, ob = O.tlwe_extract_lwe_samples(src)
+    assert (eng.to_host(ea) == oa).all() and (eng.to_host(eb) == ob).all()
+    other = G.torus32(rng, (batch, 2, 1024))
+    acc = eng.to_device(src.copy())
+    cv1 = torch.full((batch,), 0.25, dtype=torch.float32, device=acc.device)
+    cv2 = torch.full((batch,), 0.5, dtype=torch.float32, device=acc.device)
+    eng.tlwe_add_to(acc, eng.to_device(other), cv1, cv2)
+    want = (src.view(numpy.uint32) + other.view(numpy.uint32)).view(numpy.int32)
+    assert (eng.to_host(acc) == want).all() and (eng.to_host(cv1) == 0.75).all()
+    x = G.torus32(rng, (batch, 500))
+    out = eng.t32_to_phase(eng.empty(x.shape, torch.int32), eng.to_device(x), 2048)
+    assert (eng.to_host(out) == O.t32_to_phase(x, 2048)).all()
