@@ -5,7 +5,7 @@
 // threads of the CTA at the same time on 16 elements per thread, with 16 warps per SM, so that four warps
 // per scheduler share each fetched line and no thread needs more than 128 registers.
 //
-// A CTA of 512 threads owns CT = 4 ciphertexts.  Shared memory holds, per ciphertext, the accumulator
+// A CTA owns CT ciphertexts (BrCfg below).  Shared memory holds, per ciphertext, the accumulator
 // (2 x 1024 Torus32) and 4 work polynomials of 1024 field elements; a work polynomial is 16 rows of 64
 // columns (padded to 66) -- row r holds inner-transform output k1 = brev4(r), column = position along
 // the outer 64-point transform.  The transform is the factorisation of ntt_lane.cuh,
@@ -31,12 +31,29 @@ namespace nb {
 #ifndef NB_BR_CT
 #define NB_BR_CT 2
 #endif
-constexpr int BR2_CT = NB_BR_CT;                  // ciphertexts per CTA (1, 2 or 4)
-constexpr int BR2_THREADS = 128 * BR2_CT;         // 128 threads per ciphertext: every pass is 1 or 2 full sweeps
-constexpr int BR2_CTAS_PER_SM = 4 / BR2_CT;       // 16 warps per SM either way
 constexpr int ROW_STRIDE = 66;                    // u64 per row (64 + 2 padding)
 constexpr int POLY_STRIDE = 16 * ROW_STRIDE;      // u64 per work polynomial
-constexpr int BR2_POLYS = 4 * BR2_CT;             // work polynomials per CTA
+
+// Shape of one CTA of the fused bootstrap: CT ciphertexts on THREADS threads.  Per ciphertext a step has 256
+// forward tasks (4 digit polynomials x 64), 128 inverse tasks (2 polynomials x 64) and 512 MAC points pairs.
+//   BrCfg<2, 256> (default): 128 threads per ciphertext, every thread busy in every phase, 2 CTAs per SM --
+//                            the throughput shape (profiles/r1b_variants.md).
+//   BrCfg<1, 256> ("wide"):  256 threads per ciphertext: the forward phases take one sweep instead of two and the
+//                            inverse phases leave half of the warps idle; 36 % fewer instructions on the critical
+//                            path of a step.  Used when the batch fits one wave of such CTAs (latency, not throughput).
+template <int CT_, int THREADS_> struct BrCfg {
+    static constexpr int CT = CT_, THREADS = THREADS_;
+    static constexpr int POLYS = 4 * CT;                       // work polynomials per CTA
+    static constexpr int FWD_SWEEPS = 256 * CT / THREADS;      // sweeps of the forward phases
+    static constexpr int INV_TASKS = 128 * CT;                 // threads with work in the inverse phases
+    static constexpr int CTAS_PER_SM = 512 / THREADS;          // 128 registers per thread: 16 warps per SM
+    static_assert(FWD_SWEEPS >= 1 && FWD_SWEEPS * THREADS == 256 * CT && INV_TASKS <= THREADS && THREADS % 128 == 0, "shape");
+};
+constexpr int BR2_CT = NB_BR_CT;                  // ciphertexts per CTA of the default shape (1, 2 or 4)
+constexpr int BR2_THREADS = 128 * BR2_CT;
+using BrDefault = BrCfg<BR2_CT, BR2_THREADS>;
+using BrWide = BrCfg<1, 256>;
+constexpr int BR2_POLYS = BrDefault::POLYS;
 // Engine bootstrap-key row: 8 planes [(mi*2+j)*2+mo][row*64 + stored column] of plain field values plus
 // 2 correction planes K[mo] = 512 * NTT(1,...,1) * sum_{mi,j} plane, because the forward transforms run
 // on the UNSIGNED digits u = d + 512 in [0, 1023] (cheap twist, no sign handling):
@@ -240,7 +257,7 @@ NB_HD void phase_inv3(int p, int row, int u, u64 *w_all)
 // ---- MAC: thread = (row, pair q): stored columns 2q, 2q+1 of every work polynomial -----------------
 // bk_row: internal layout [mi][j][mo][row * 64 + stored column], plain (non-Montgomery) values.
 // out polynomial mo of ciphertext ct overwrites work polynomial ct*4 + mo.
-NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64 *bk_row)
+template <int CT> NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64 *bk_row)
 {
     const int pos = row * 64 + 2 * q;
     u64 bk[BK_PLANES][2];
@@ -248,7 +265,7 @@ NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64 *bk_row)
         constexpr int m = decltype(M)::value;            // m = (mi * 2 + j) * 2 + mo; 8 + mo = correction
         ld2_global(bk_row + m * NTT_N + pos, bk[m][0], bk[m][1]);
     });
-    for (int ct = 0; ct < BR2_CT; ct++) {
+    for (int ct = 0; ct < CT; ct++) {
         u64 *w = w_all + ct * 4 * POLY_STRIDE + row * ROW_STRIDE + 2 * q;
         u64 f[4][2];
         static_for<0, 4>([&](auto D) {
@@ -269,10 +286,10 @@ NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64 *bk_row)
     }
 }
 
-// all 16 rows x 32 pairs, BR2_THREADS threads
-NB_HD void phase_mac(int tid, u64 *w_all, const u64 *bk_row)
+// all 16 rows x 32 pairs, Cfg::THREADS threads
+template <class Cfg = BrDefault> NB_HD void phase_mac(int tid, u64 *w_all, const u64 *bk_row)
 {
-    for (int row = tid >> 5; row < 16; row += BR2_THREADS / 32) phase_mac_row(row, tid & 31, w_all, bk_row);
+    for (int row = tid >> 5; row < 16; row += Cfg::THREADS / 32) phase_mac_row<Cfg::CT>(row, tid & 31, w_all, bk_row);
 }
 
 // ---- inv1: task = (ct, mo, j2): reads W[ct*4+mo], writes ACC[ct][mo] --------------------------------
@@ -349,32 +366,34 @@ NB_HD void phase_inv1_generic(int task, u64 *y, const u64 *w_all, const u64 *twd
     });
 }
 
-// thread -> task maps (tid in [0, 512), it = iteration)
-NB_HD void map_fwd2(int tid, int it, int &p, int &row, int &g)
+// thread -> task maps (it = sweep).  The inverse maps return false for threads without a task (whole warps).
+template <class Cfg = BrDefault> NB_HD void map_fwd2(int tid, int it, int &p, int &row, int &g)
 {
-    constexpr int Q = BR2_THREADS / 4;                 // threads per value of g (>= 32: g is warp-uniform)
+    constexpr int Q = Cfg::THREADS / 4;                // threads per value of g (>= 32: g is warp-uniform)
     g = tid / Q;
     int x = it * Q + (tid % Q);
     p = x >> 4; row = x & 15;
 }
-NB_HD void map_fwd3(int tid, int it, int &p, int &row, int &u)
+template <class Cfg = BrDefault> NB_HD void map_fwd3(int tid, int it, int &p, int &row, int &u)
 {
-    u = tid & 3; row = (tid >> 2) & 15; p = it * (BR2_THREADS / 64) + (tid >> 6);
+    u = tid & 3; row = (tid >> 2) & 15; p = it * (Cfg::THREADS / 64) + (tid >> 6);
 }
 // inverse passes act on polynomials ct*4 + mo only (half of the work polynomials)
-NB_HD void map_inv2(int tid, int &p, int &row, int &g)
+template <class Cfg = BrDefault> NB_HD bool map_inv2(int tid, int &p, int &row, int &g)
 {
-    constexpr int Q = BR2_THREADS / 4;
+    constexpr int Q = Cfg::THREADS / 4;
     g = tid / Q;
     int x = tid % Q;                                   // 2 CT polys x 16 rows
     int pp = x >> 4; row = x & 15;
     p = (pp >> 1) * 4 + (pp & 1);
+    return x < 32 * Cfg::CT;
 }
-NB_HD void map_inv3(int tid, int &p, int &row, int &u)
+template <class Cfg = BrDefault> NB_HD bool map_inv3(int tid, int &p, int &row, int &u)
 {
     u = tid & 3; row = (tid >> 2) & 15;
     int pp = tid >> 6;
     p = (pp >> 1) * 4 + (pp & 1);
+    return pp < 2 * Cfg::CT;
 }
 
 }  // namespace nb

@@ -16,6 +16,7 @@ struct nb_ctx {
     u64 *d_ones512;                      // 512 * NTT(all-ones), natural order (bk_prepare)
     int sm_count;
     int stagger_cycles;
+    size_t wide_max;                     // largest batch launched in the wide (1 ciphertext / 256 threads) shape
     std::string err;
 };
 
@@ -68,8 +69,14 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     NB_TRY(check(ctx, cudaMemcpy(ctx->d_ph_inv, pt.inv.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
     NB_TRY(check(ctx, cudaMalloc(&ctx->d_ones512, NTT_N * sizeof(u64)), "cudaMalloc"));
     NB_TRY(check(ctx, cudaMemcpy(ctx->d_ones512, pt.ones512.data(), NTT_N * sizeof(u64), cudaMemcpyHostToDevice), "memcpy"));
-    NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)BR2_SMEM_BYTES), "cudaFuncSetAttribute(blind_rotate)"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel<BrDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)br_smem_bytes<BrDefault>()), "cudaFuncSetAttribute(blind_rotate)"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel<BrWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)br_smem_bytes<BrWide>()), "cudaFuncSetAttribute(blind_rotate wide)"));
+    {   // batches that fit one wave of wide CTAs (one ciphertext on 256 threads) take the low-latency shape
+        const char *e = getenv("NUFHE_B200_WIDE_MAX");
+        ctx->wide_max = e ? (size_t)atoll(e) : (size_t)ctx->sm_count * BrWide::CTAS_PER_SM;
+    }
     NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
@@ -109,7 +116,7 @@ const char *nb_build_info(void)
     if (info.empty()) {
         char buf[512];
         cudaFuncAttributes a{}, b{}, c{};
-        cudaFuncGetAttributes(&a, blind_rotate_kernel);
+        cudaFuncGetAttributes(&a, blind_rotate_kernel<BrDefault>);
         cudaFuncGetAttributes(&b, ntt_forward_kernel<true>);
         cudaFuncGetAttributes(&c, keyswitch_kernel);
         snprintf(buf, sizeof(buf),
@@ -195,6 +202,20 @@ int nb_bk_prepare(nb_ctx *ctx, const uint64_t *bk_ref, uint64_t *bk_int, size_t 
     return launch_check(ctx, "bk_prepare_kernel");
 }
 
+// One launch of the fused kernel in the shape that suits the batch: up to one wave of "wide" CTAs (1 ciphertext on
+// 256 threads, shortest step) for small batches, else 2 ciphertexts per CTA (highest throughput).
+static void launch_br(nb_ctx *ctx, const BlindRotateArgs &p)
+{
+    if (p.batch <= ctx->wide_max) {
+        blind_rotate_kernel<BrWide><<<(int)p.batch, BrWide::THREADS, br_smem_bytes<BrWide>(), ctx->stream>>>(
+            p, ctx->d_ph_fwd, ctx->d_ph_inv);
+    } else {
+        const int grid = (int)((p.batch + BrDefault::CT - 1) / BrDefault::CT);
+        blind_rotate_kernel<BrDefault><<<grid, BrDefault::THREADS, br_smem_bytes<BrDefault>(), ctx->stream>>>(
+            p, ctx->d_ph_fwd, ctx->d_ph_inv);
+    }
+}
+
 int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, size_t bk_row, size_t batch)
 {
     if (!ctx || !accum || !bk_int) return fail(ctx, NB_EINVAL, "nb_external_product: null argument");
@@ -203,8 +224,7 @@ int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, siz
     BlindRotateArgs p{};
     p.accum = accum; p.accum_out = accum; p.bk = (const u64 *)bk_int + bk_row * BK_ROW_U64;
     p.plain = 1; p.batch = batch; p.sm_count = ctx->sm_count; p.stagger_cycles = 0;
-    int grid = (int)((batch + BR2_CT - 1) / BR2_CT);
-    blind_rotate_kernel<<<grid, BR2_THREADS, BR2_SMEM_BYTES, ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);
+    launch_br(ctx, p);
     return launch_check(ctx, "blind_rotate_kernel(plain external product)");
 }
 
@@ -213,10 +233,9 @@ static int launch_blind_rotate(nb_ctx *ctx, BlindRotateArgs &p)
     if (p.n <= 0 || p.n > LWE_N_MAX) return fail(ctx, NB_EUNSUPPORTED, "LWE dimension out of range");
     if (p.batch == 0) return NB_OK;
     NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
-    int grid = (int)((p.batch + BR2_CT - 1) / BR2_CT);
     p.sm_count = ctx->sm_count;
     p.stagger_cycles = ctx->stagger_cycles;
-    blind_rotate_kernel<<<grid, BR2_THREADS, BR2_SMEM_BYTES, ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);
+    launch_br(ctx, p);
     return launch_check(ctx, "blind_rotate_kernel");
 }
 

@@ -50,11 +50,13 @@ void emul_ntt_inverse(const u64 *in, u64 *out, size_t batch)
 // amounts per ciphertext or NULL (plain external product, overwrite).
 int emul_phase_ct(void) { return BR2_CT; }
 
-void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct)
+}  // extern "C"
+
+template <class Cfg> static void phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct)
 {
     static PhaseTables T;
-    std::vector<i32> acc(BR2_CT * 2 * NTT_N, 0);
-    std::vector<u64> w(BR2_POLYS * POLY_STRIDE, 0);
+    std::vector<i32> acc(Cfg::CT * 2 * NTT_N, 0);
+    std::vector<u64> w(Cfg::POLYS * POLY_STRIDE, 0);
     std::vector<u64> bk(BK_ROW_U64);
     for (int c = 0; c < nct; c++) memcpy(&acc[c * 2 * NTT_N], acc_io + c * 2 * NTT_N, sizeof(i32) * 2 * NTT_N);
     int rots[4] = {0, 0, 0, 0};
@@ -70,23 +72,36 @@ void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct
         }
         for (int mo = 0; mo < 2; mo++) bk[(8 + mo) * NTT_N + pos] = ff_mul(sum[mo], T.ones512[k]);
     }
-    for (int it = 0; it < 2; it++)
-        for (int tid = 0; tid < BR2_THREADS; tid++) {
-            if (rot) phase_fwd1<true>(it * BR2_THREADS + tid, acc.data(), w.data(), T.fwd.data(), rots);
-            else phase_fwd1<false>(it * BR2_THREADS + tid, acc.data(), w.data(), T.fwd.data(), rots);
+    constexpr int TH = Cfg::THREADS;
+    for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
+        for (int tid = 0; tid < TH; tid++) {
+            if (rot) phase_fwd1<true>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
+            else phase_fwd1<false>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
         }
-    for (int it = 0; it < 2; it++)
-        for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, g; map_fwd2(tid, it, p, r, g); phase_fwd2(p, r, g, w.data()); }
-    for (int it = 0; it < 2; it++)
-        for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, u; map_fwd3(tid, it, p, r, u); phase_fwd3(p, r, u, w.data()); }
-    for (int tid = 0; tid < BR2_THREADS; tid++) phase_mac(tid, w.data(), bk.data());
-    for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, u; map_inv3(tid, p, r, u); phase_inv3(p, r, u, w.data()); }
-    for (int tid = 0; tid < BR2_THREADS; tid++) { int p, r, g; map_inv2(tid, p, r, g); phase_inv2(p, r, g, w.data()); }
-    for (int tid = 0; tid < BR2_THREADS; tid++) {
+    for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
+        for (int tid = 0; tid < TH; tid++) { int p, r, g; map_fwd2<Cfg>(tid, it, p, r, g); phase_fwd2(p, r, g, w.data()); }
+    for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
+        for (int tid = 0; tid < TH; tid++) { int p, r, u; map_fwd3<Cfg>(tid, it, p, r, u); phase_fwd3(p, r, u, w.data()); }
+    for (int tid = 0; tid < TH; tid++) phase_mac<Cfg>(tid, w.data(), bk.data());
+    for (int tid = 0; tid < TH; tid++) { int p, r, u; if (map_inv3<Cfg>(tid, p, r, u)) phase_inv3(p, r, u, w.data()); }
+    for (int tid = 0; tid < TH; tid++) { int p, r, g; if (map_inv2<Cfg>(tid, p, r, g)) phase_inv2(p, r, g, w.data()); }
+    for (int tid = 0; tid < Cfg::INV_TASKS; tid++) {
         if (rot) phase_inv1<true>(tid, acc.data(), w.data(), T.inv.data());
         else phase_inv1<false>(tid, acc.data(), w.data(), T.inv.data());
     }
     for (int c = 0; c < nct; c++) memcpy(acc_io + c * 2 * NTT_N, &acc[c * 2 * NTT_N], sizeof(i32) * 2 * NTT_N);
+}
+
+extern "C" {
+
+void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct)
+{
+    phase_step<BrDefault>(acc_io, bk_ref_row, rot, nct);
+}
+// the wide shape (one ciphertext on 256 threads)
+void emul_phase_step_wide(i32 *acc_io, const u64 *bk_ref_row, const int *rot)
+{
+    phase_step<BrWide>(acc_io, bk_ref_row, rot, 1);
 }
 
 void emul_ff_shl_var(const u64 *in, const int *s, u64 *out, size_t n)

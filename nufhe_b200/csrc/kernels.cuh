@@ -167,10 +167,12 @@ __global__ void bk_prepare_kernel(const u64 *__restrict__ bk_ref, u64 *__restric
 NB_HD i32 modswitch_2n(i32 x) { return (i32)(((u32)x + (1u << 20)) >> 21); }
 
 // ---- fused bootstrap: CTA-wide phases over shared-memory-resident polynomials (br_phases.cuh) -----
-constexpr size_t BR2_SMEM_ACC = (size_t)BR2_CT * 2 * NTT_N * sizeof(i32);
-constexpr size_t BR2_SMEM_W = (size_t)BR2_POLYS * POLY_STRIDE * sizeof(u64);
-constexpr size_t BR2_SMEM_TWD = 2 * NTT_N * sizeof(u64);
-constexpr size_t BR2_SMEM_BYTES = BR2_SMEM_ACC + BR2_SMEM_W + BR2_SMEM_TWD + 64;
+template <class Cfg> constexpr size_t br_smem_bytes()
+{
+    return (size_t)Cfg::CT * 2 * NTT_N * sizeof(i32) + (size_t)Cfg::POLYS * POLY_STRIDE * sizeof(u64) +
+           2 * NTT_N * sizeof(u64) + 64;
+}
+constexpr size_t BR2_SMEM_BYTES = br_smem_bytes<BrDefault>();
 
 struct BlindRotateArgs {
     // mode A (gate): x = c + s1 * in1 + s2 * in2 is formed on the fly (gates.py prologues), then
@@ -203,14 +205,14 @@ struct Br2Smem {
     int *rot;      // [2][CT]
 };
 
-NB_D Br2Smem br2_carve(unsigned char *raw)
+template <class Cfg> NB_D Br2Smem br2_carve(unsigned char *raw)
 {
     Br2Smem s;
     s.w = reinterpret_cast<u64 *>(raw);
-    s.twd_fwd = s.w + BR2_POLYS * POLY_STRIDE;
+    s.twd_fwd = s.w + Cfg::POLYS * POLY_STRIDE;
     s.twd_inv = s.twd_fwd + NTT_N;
     s.acc = reinterpret_cast<i32 *>(s.twd_inv + NTT_N);
-    s.rot = reinterpret_cast<int *>(s.acc + BR2_CT * 2 * NTT_N);
+    s.rot = reinterpret_cast<int *>(s.acc + Cfg::CT * 2 * NTT_N);
     return s;
 }
 
@@ -227,55 +229,56 @@ NB_D int br2_rotation(const BlindRotateArgs &p, size_t c, int i)
     return modswitch_2n(xa);
 }
 
-template <bool ROTATE>
+template <bool ROTATE, class Cfg>
 NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *rot, int tid)
 {
-    // forward transforms of the 16 digit polynomials (4 ciphertexts x 2 polynomials x 2 digits)
+    // forward transforms of the digit polynomials (CT ciphertexts x 2 polynomials x 2 digits)
 #pragma unroll 1
-    for (int it = 0; it < 2; it++) phase_fwd1<ROTATE>(it * BR2_THREADS + tid, s.acc, s.w, s.twd_fwd, rot);
+    for (int it = 0; it < Cfg::FWD_SWEEPS; it++) phase_fwd1<ROTATE>(it * Cfg::THREADS + tid, s.acc, s.w, s.twd_fwd, rot);
     __syncthreads();
 #pragma unroll 1
-    for (int it = 0; it < 2; it++) { int p, r, g; map_fwd2(tid, it, p, r, g); phase_fwd2(p, r, g, s.w); }
+    for (int it = 0; it < Cfg::FWD_SWEEPS; it++) { int p, r, g; map_fwd2<Cfg>(tid, it, p, r, g); phase_fwd2(p, r, g, s.w); }
     __syncthreads();
 #pragma unroll 1
-    for (int it = 0; it < 2; it++) { int p, r, u; map_fwd3(tid, it, p, r, u); phase_fwd3(p, r, u, s.w); }
+    for (int it = 0; it < Cfg::FWD_SWEEPS; it++) { int p, r, u; map_fwd3<Cfg>(tid, it, p, r, u); phase_fwd3(p, r, u, s.w); }
     __syncthreads();
     // multiply-accumulate with the key row (tgsw_gpu.py:58-107); each key element is fetched once per CTA
-    phase_mac(tid, s.w, bk_row);
+    phase_mac<Cfg>(tid, s.w, bk_row);
     __syncthreads();
-    // inverse transforms of the 8 output polynomials
-    { int p, r, u; map_inv3(tid, p, r, u); phase_inv3(p, r, u, s.w); }
+    // inverse transforms of the output polynomials (threads beyond Cfg::INV_TASKS idle: whole warps)
+    { int p, r, u; if (map_inv3<Cfg>(tid, p, r, u)) phase_inv3(p, r, u, s.w); }
     __syncthreads();
-    { int p, r, g; map_inv2(tid, p, r, g); phase_inv2(p, r, g, s.w); }
+    { int p, r, g; if (map_inv2<Cfg>(tid, p, r, g)) phase_inv2(p, r, g, s.w); }
     __syncthreads();
-    phase_inv1<ROTATE>(tid, s.acc, s.w, s.twd_inv);
+    if (tid < Cfg::INV_TASKS) phase_inv1<ROTATE>(tid, s.acc, s.w, s.twd_inv);
 }
 
-__global__ void __launch_bounds__(BR2_THREADS, BR2_CTAS_PER_SM) blind_rotate_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g,
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g,
                                                                        const u64 *__restrict__ twd_inv_g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Br2Smem s = br2_carve(smem_raw);
+    const Br2Smem s = br2_carve<Cfg>(smem_raw);
     const int tid = threadIdx.x;
-    for (int i = tid; i < NTT_N; i += BR2_THREADS) { s.twd_fwd[i] = twd_fwd_g[i]; s.twd_inv[i] = twd_inv_g[i]; }
+    for (int i = tid; i < NTT_N; i += Cfg::THREADS) { s.twd_fwd[i] = twd_fwd_g[i]; s.twd_inv[i] = twd_inv_g[i]; }
 
-    // Two CTAs share an SM (BR2_CTAS_PER_SM).  Optional start-up stagger so that the pair runs out of phase
+    // Two CTAs share an SM (Cfg::CTAS_PER_SM).  Optional start-up stagger so that the pair runs out of phase
     // (MAC is IMAD-heavy, the transform passes IADD3-heavy).  Measured on B200: no gain -- the kernel sits at
     // the ALU pipe's ceiling either way (profiles/r1_v23_*) -- so ctx->stagger_cycles defaults to 0.
-    if (BR2_CTAS_PER_SM > 1 && p.stagger_cycles > 0 && ((blockIdx.x / p.sm_count) & 1) &&
-        blockIdx.x < (unsigned)(BR2_CTAS_PER_SM * p.sm_count)) {
+    if (Cfg::CTAS_PER_SM > 1 && p.stagger_cycles > 0 && ((blockIdx.x / p.sm_count) & 1) &&
+        blockIdx.x < (unsigned)(Cfg::CTAS_PER_SM * p.sm_count)) {
         if (tid == 0) {
             const long long t0 = clock64();
             while (clock64() - t0 < p.stagger_cycles) { }
         }
         __syncthreads();
     }
-    const size_t ct0 = (size_t)blockIdx.x * BR2_CT;
+    const size_t ct0 = (size_t)blockIdx.x * Cfg::CT;
     // ciphertext slots beyond the batch replay the last ciphertext and store nothing
     auto ct_of = [&](int slot) { size_t c = ct0 + slot; return c < p.batch ? c : p.batch - 1; };
 
     // accumulator initialisation: 8 polynomials x 1024 coefficients
-    for (int e = tid; e < BR2_CT * 2 * NTT_N; e += BR2_THREADS) {
+    for (int e = tid; e < Cfg::CT * 2 * NTT_N; e += Cfg::THREADS) {
         const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);
         const size_t c = ct_of(slot);
         i32 val;
@@ -299,21 +302,21 @@ __global__ void __launch_bounds__(BR2_THREADS, BR2_CTAS_PER_SM) blind_rotate_ker
     }
     if (p.plain) {
         __syncthreads();
-        br2_step<false>(s, p.bk, s.rot, tid);
+        br2_step<false, Cfg>(s, p.bk, s.rot, tid);
         __syncthreads();
     } else {
-        if (tid < BR2_CT) s.rot[tid] = br2_rotation(p, ct_of(tid), 0);
+        if (tid < Cfg::CT) s.rot[tid] = br2_rotation(p, ct_of(tid), 0);
         __syncthreads();
         for (int i = 0; i < p.n; i++) {
             int next = 0;
-            if (tid < BR2_CT && i + 1 < p.n) next = br2_rotation(p, ct_of(tid), i + 1);
-            br2_step<true>(s, p.bk + (size_t)i * BK_ROW_U64, s.rot + (i & 1) * BR2_CT, tid);
-            if (tid < BR2_CT) s.rot[((i + 1) & 1) * BR2_CT + tid] = next;
+            if (tid < Cfg::CT && i + 1 < p.n) next = br2_rotation(p, ct_of(tid), i + 1);
+            br2_step<true, Cfg>(s, p.bk + (size_t)i * BK_ROW_U64, s.rot + (i & 1) * Cfg::CT, tid);
+            if (tid < Cfg::CT) s.rot[((i + 1) & 1) * Cfg::CT + tid] = next;
             __syncthreads();
         }
     }
 
-    for (int e = tid; e < BR2_CT * 2 * NTT_N; e += BR2_THREADS) {
+    for (int e = tid; e < Cfg::CT * 2 * NTT_N; e += Cfg::THREADS) {
         const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);
         const size_t c = ct0 + slot;
         if (c >= p.batch) continue;

@@ -115,3 +115,28 @@ def test_full_size_batches_decrypt_to_truth_table(eng, keys, dev_keys, batch):
     u1, u2 = eng.bootstrap_extract2((d[0], d[1], and_const, 1, 1), (d[0], d[2], and_const, -1, 1), O.MU, bk_int)
     ma, mb, _ = eng.keyswitch(ks, u1, u2, c=O.phase_to_t32(1, 8))
     assert (keys.decrypt((eng.to_host(ma), eng.to_host(mb))) == numpy.where(bits[0], bits[1], bits[2])).all()
+
+
+def test_both_cta_shapes_give_the_same_bits(keys, monkeypatch):
+    """The fused kernel has two CTA shapes (2 ciphertexts per 256 threads; 1 ciphertext per 256 threads for batches
+    that fit one wave).  Force each shape for the same inputs, including a ragged batch and one larger than a wave
+    of wide CTAs; both must equal the oracle."""
+    from nufhe_b200.engine import Engine
+    rng = G.rs(480)
+    outs = {}
+    for B in (1, 5, 301):
+        bits_a, bits_b = rng.randint(0, 2, B).astype(bool), rng.randint(0, 2, B).astype(bool)
+        a, b = keys.encrypt(bits_a), keys.encrypt(bits_b)
+        want = O.gate_binary('nand', a, b, keys.bk, keys.ks) if B <= 5 else None
+        for wide_max in ('0', '1000000'):
+            monkeypatch.setenv('NUFHE_B200_WIDE_MAX', wide_max)
+            eng = Engine()
+            dk = (eng.bk_prepare(eng.to_device(keys.bk)),
+                  (eng.to_device(keys.ks_a), eng.to_device(keys.ks_b), eng.to_device(keys.ks_cv)))
+            ext, out = gpu_gate(eng, dk, 'nand', a, b)
+            outs[(B, wide_max)] = (ext, out)
+            if want is not None:
+                assert (out[0] == want[0]).all() and (out[1] == want[1]).all(), (B, wide_max)
+            assert (keys.decrypt(out) == ~(bits_a & bits_b)).all()
+        for x, y in zip(outs[(B, '0')], outs[(B, '1000000')]):
+            assert (x[0] == y[0]).all() and (x[1] == y[1]).all(), B

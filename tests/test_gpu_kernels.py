@@ -237,3 +237,28 @@ def test_multi_kernel_steps_vs_oracle(eng, batch):
     x = G.torus32(rng, (batch, 500))
     out = eng.t32_to_phase(eng.empty(x.shape, torch.int32), eng.to_device(x), 2048)
     assert (eng.to_host(out) == O.t32_to_phase(x, 2048)).all()
+
+
+def test_transform_interface(eng):
+    """nufhe's `Transform` / `ForwardTransform` / `InverseTransform` (transform/computation.py:28-99,
+    polynomial_transform_ntt.py:120-131) on top of the stand-alone kernels."""
+    from nufhe_b200.transform import Transform, ForwardTransform, InverseTransform, get_transform
+    rng = G.rs(41)
+    x = G.torus32(rng, (3, 5, 1024))
+    fwd = ForwardTransform((3, 5), 1024, None).compile(eng)
+    inv = InverseTransform((3, 5), 1024, None).compile(eng)
+    tr = eng.empty((3, 5, 1024), torch.int64)
+    fwd(tr, eng.to_device(x))
+    assert (eng.to_host(tr, True) == O.ntt_forward_i32(x.reshape(15, 1024)).reshape(3, 5, 1024)).all()
+    back = eng.empty((3, 5, 1024), torch.int32)
+    inv(back, tr)
+    assert (eng.to_host(back) == x).all()
+    ff = G.ff_numbers(rng, (4, 1024))
+    t2 = Transform(None, (4,), kernel_repetitions=2).compile(eng)
+    out = eng.empty((4, 1024), torch.int64)
+    t2(out, dev_u64(eng, ff))
+    assert (eng.to_host(out, True) == O.ntt_forward_u64(ff)).all()
+    with pytest.raises(ValueError):
+        t2(out, dev_u64(eng, ff[:2]))
+    with pytest.raises(ValueError):
+        get_transform('FFT')

@@ -79,7 +79,9 @@ def enclosing_functions(path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--lib', default=os.path.join(ROOT, 'nufhe_b200', 'csrc', 'libnufhe_b200.so'))
-    ap.add_argument('--kernel', default='blind_rotate_kernel')
+    ap.add_argument('--kernel', default='blind_rotate_kernelINS_5BrCfgILi2ELi256',
+                    help='substring of the mangled kernel name (default: the 2-ciphertext shape; the wide shape is '
+                         'blind_rotate_kernelINS_5BrCfgILi1ELi256)')
     ap.add_argument('--by-func', action='store_true', help='also split each phase by innermost ff.cuh / br_phases function')
     ap.add_argument('--opcodes', action='store_true', help='per-step histogram of instruction forms (carry-out variants split)')
     args = ap.parse_args()
@@ -104,7 +106,7 @@ def main():
                 phase_lines[i] = m.group(1)
             if line.startswith('}'):
                 in_step = False
-    step_call_lines = [i for i, l in enumerate(ksrc, 1) if 'br2_step<true>' in l and 'void' not in l]
+    step_call_lines = [i for i, l in enumerate(ksrc, 1) if 'br2_step<true' in l and 'void' not in l]
 
     # lines of br_phases.cuh inside a `switch (g)` (warp-uniform 4-way): each branch runs for a quarter of the warps
     bpath = os.path.join(ROOT, 'nufhe_b200', 'csrc', 'br_phases.cuh')
