@@ -124,6 +124,16 @@ int nb_tlwe_extract_lwe_samples(nb_ctx *ctx, int32_t *out_a, int32_t *out_b, con
 /* t32_to_phase (numeric_functions.py:34-36, kernel numeric_functions_gpu.py:39-77): the mod-switch of bootstrap()
  * (bootstrap.py:216-219) as a separate step; mspace_size must divide 2^32 */
 int nb_t32_to_phase(nb_ctx *ctx, int32_t *out, const int32_t *in, size_t n, uint32_t mspace_size);
+/* The external product of the multi-kernel path step by step (TGswTransformedExternalMul, tgsw_gpu.py:110-169), for
+ * any TLWE mask size k and decomposition length l -- the fused kernel covers k = 1, l = 2 only:
+ * decompose -> nb_ntt_forward_i32 -> MAC -> nb_ntt_inverse_i32.
+ * nb_tgsw_decompose (tgsw_gpu.py:31-54): out (polys, l, N) from in (polys, N); offset = TGswParams.offset.
+ * nb_tgsw_mac (tgsw_gpu.py:58-107): out (B, k+1, 1024) = sum_{mi,j} mul_prepared(tr (B, k+1, l, 1024),
+ * bk_row (k+1, l, k+1, 1024)), bk_row in the reference's layout (natural order, Montgomery form). */
+int nb_tgsw_decompose(nb_ctx *ctx, int32_t *out, const int32_t *in, size_t polys, int decomp_length, int bs_log2_base,
+                      int32_t offset, int n_log2);
+int nb_tgsw_mac(nb_ctx *ctx, uint64_t *out, const uint64_t *tr, const uint64_t *bk_row, size_t batch, int mask_size,
+                int decomp_length);
 /* tlwe_add_to (tlwe.py:173-175): res += src (int32 wrap-around, n elements); variances (n_cv floats, may be NULL) */
 int nb_tlwe_add_to(nb_ctx *ctx, int32_t *res, const int32_t *src, size_t n, float *res_cv, const float *src_cv,
                    size_t n_cv);

@@ -46,6 +46,8 @@ SIGNATURES = {
     'nb_tlwe_extract_lwe_samples': [_vp, _vp, _vp, _vp, _int, _int, _sz],
     'nb_tlwe_add_to': [_vp, _vp, _vp, _sz, _vp, _vp, _sz],
     'nb_t32_to_phase': [_vp, _vp, _vp, _sz, ctypes.c_uint32],
+    'nb_tgsw_decompose': [_vp, _vp, _vp, _sz, _int, _int, _i32, _int],
+    'nb_tgsw_mac': [_vp, _vp, _vp, _vp, _sz, _int, _int],
 }
 _RESTYPES = {'nb_bk_row_u64': ctypes.c_size_t, 'nb_ctx_destroy': None, 'nb_last_error': ctypes.c_char_p, 'nb_build_info': ctypes.c_char_p}
 

@@ -17,7 +17,8 @@ class NuFHEParameters:
 
     :param transform_type: only ``'NTT'`` is built here (the integer, bit-exact transform);
         ``'FFT'`` raises ``ValueError``.
-    :param tlwe_mask_size: only 1 (the reference's single-kernel path has the same limit,
+    :param tlwe_mask_size: the TLWE mask size k.  1 (default) runs on the fused bootstrap kernel; larger values run
+        on the multi-kernel path, like in the reference (its single-kernel path has the same limit,
         blind_rotate.py:53-58).
     """
 
@@ -26,8 +27,6 @@ class NuFHEParameters:
         assert tlwe_mask_size >= 1
         if transform_type != 'NTT':
             raise ValueError("nufhe_b200 implements the NTT transform only")
-        if tlwe_mask_size != 1:
-            raise ValueError("nufhe_b200 implements tlwe_mask_size=1 only")
 
         tlwe_polynomial_degree = 1024
         lwe_size = 500

@@ -90,8 +90,13 @@ def bootstrap_affine(thr, result: LweSampleArray, bk: BootstrapKey, ks: LweKeysw
         _keyswitch_into(thr, result, ks, ext_sample, None, 0)
 
 
-def _single_kernel(perf_params):
-    return perf_params is None or getattr(perf_params, 'single_kernel_bootstrap', True) is not False
+def _single_kernel(perf_params, bk=None):
+    """Which bootstrap path to take.  Without explicit performance parameters: the fused kernel whenever the key's
+    parameters allow it (what `PerformanceParameters(params).for_device(...)` would say)."""
+    from .tgsw import fused_kernel_supported
+    if perf_params is None:
+        return bk is None or fused_kernel_supported(bk.bk_params)
+    return getattr(perf_params, 'single_kernel_bootstrap', True) is not False
 
 
 def mux_rotate(thr, result: TLweSampleArray, accum: TLweSampleArray, bki: TransformedTGswSampleArray, bk_idx: int,
@@ -128,7 +133,7 @@ def blind_rotate_and_extract(thr, result: LweSampleArray, v: TorusPolynomialArra
     shift_tp_inverted_power(thr, testvectbis, barb, v)
     acc = TLweSampleArray.empty(thr, accum_params, shape)
     tlwe_noiseless_trivial(thr, acc, testvectbis)
-    if _single_kernel(perf_params):
+    if _single_kernel(perf_params, bk):
         BlindRotate_gpu(result, acc, bk, ks, bara, perf_params, no_keyswitch=no_keyswitch, thr=thr)
     else:
         blind_rotate(thr, acc, bk, bara, bk.in_out_params.size, bk.bk_params, perf_params)
@@ -143,7 +148,7 @@ def bootstrap(thr, result: LweSampleArray, bk: BootstrapKey, ks: LweKeyswitchKey
     Default: one fused kernel (+ key switch).  `single_kernel_bootstrap=False`: the reference's sequence of
     separate steps -- mod-switch, test vector, rotation of the test vector, trivial sample, 500 x 3 launches,
     extraction, key switch -- with bit-identical results (tests/test_gpu_api.py)."""
-    if _single_kernel(perf_params):
+    if _single_kernel(perf_params, bk):
         bootstrap_affine(thr, result, bk, ks, mu, x, None, 0, 1, 0, no_keyswitch=no_keyswitch)
         return
     N = bk.accum_params.polynomial_degree

@@ -382,6 +382,33 @@ int nb_t32_to_phase(nb_ctx *ctx, int32_t *out, const int32_t *in, size_t n, uint
     return launch_check(ctx, "t32_to_phase_kernel");
 }
 
+int nb_tgsw_decompose(nb_ctx *ctx, int32_t *out, const int32_t *in, size_t polys, int decomp_length, int bs_log2_base,
+                      int32_t offset, int n_log2)
+{
+    if (!ctx) return NB_EINVAL;
+    if (!out || !in) return fail(ctx, NB_EINVAL, "nb_tgsw_decompose: null argument");
+    if (decomp_length < 1 || bs_log2_base < 1 || decomp_length * bs_log2_base > 32 || n_log2 < 1 || n_log2 > 20)
+        return fail(ctx, NB_EINVAL, "nb_tgsw_decompose: bad decomposition");
+    if (polys == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    tgsw_decompose_kernel<<<ew_grid(ctx, (polys * decomp_length) << n_log2), 256, 0, ctx->stream>>>(
+        out, in, polys, decomp_length, bs_log2_base, offset, n_log2);
+    return launch_check(ctx, "tgsw_decompose_kernel");
+}
+
+int nb_tgsw_mac(nb_ctx *ctx, uint64_t *out, const uint64_t *tr, const uint64_t *bk_row, size_t batch, int mask_size,
+                int decomp_length)
+{
+    if (!ctx) return NB_EINVAL;
+    if (!out || !tr || !bk_row) return fail(ctx, NB_EINVAL, "nb_tgsw_mac: null argument");
+    if (mask_size < 1 || mask_size > 15 || decomp_length < 1 || decomp_length > 32) return fail(ctx, NB_EINVAL, "nb_tgsw_mac: bad size");
+    if (batch == 0) return NB_OK;
+    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    tgsw_mac_kernel<<<ew_grid(ctx, batch * (mask_size + 1) * NTT_N), 256, 0, ctx->stream>>>(
+        (u64 *)out, (const u64 *)tr, (const u64 *)bk_row, batch, mask_size + 1, decomp_length);
+    return launch_check(ctx, "tgsw_mac_kernel");
+}
+
 int nb_tlwe_add_to(nb_ctx *ctx, int32_t *res, const int32_t *src, size_t n, float *res_cv, const float *src_cv,
                    size_t n_cv)
 {

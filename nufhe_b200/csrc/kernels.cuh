@@ -399,6 +399,46 @@ __global__ void t32_to_phase_kernel(i32 *__restrict__ out, const i32 *__restrict
         out[i] = (i32)(((u32)in[i] + half) / interv);
 }
 
+// Gadget decomposition as its own kernel (TGswPolynomialDecompH, tgsw_gpu.py:31-54; tgsw_cpu.py:26-49):
+// out[poly][j][x] = (((in[poly][x] + offset) >> (32 - (j + 1) bg_bit)) & (Bg - 1)) - Bg / 2
+__global__ void tgsw_decompose_kernel(i32 *__restrict__ out, const i32 *__restrict__ in, size_t polys, int decomp_length,
+                                      int bs_log2_base, i32 offset, int n_log2)
+{
+    const int N = 1 << n_log2;
+    const size_t total = (polys * decomp_length) << n_log2;
+    const u32 mask = (1u << bs_log2_base) - 1u, half = 1u << (bs_log2_base - 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i & (N - 1));
+        const size_t pj = i >> n_log2;
+        const int j = (int)(pj % decomp_length);
+        const size_t poly = pj / decomp_length;
+        const u32 t = (u32)in[(poly << n_log2) + x] + (u32)offset;
+        out[i] = (i32)(((t >> (32 - (j + 1) * bs_log2_base)) & mask) - half);
+    }
+}
+
+// The point-wise multiply-accumulate of the external product as its own kernel, on the reference's key layout
+// (tgsw_gpu.py:58-107; tgsw_cpu.py:52-79): out[b][mo][x] = sum_{mi, j} mul_prepared(tr[b][mi][j][x], bk[mi][j][mo][x])
+// for any mask size k (mi, mo <= k) and decomposition length.  bk_row: (k+1, l, k+1, N), Montgomery form.
+__global__ void tgsw_mac_kernel(u64 *__restrict__ out, const u64 *__restrict__ tr, const u64 *__restrict__ bk_row,
+                                size_t batch, int k1, int decomp_length)
+{
+    const size_t total = batch * k1 * NTT_N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i & (NTT_N - 1));
+        const int mo = (int)((i >> 10) % k1);
+        const size_t b = (i >> 10) / k1;
+        u64 acc = 0;
+        for (int mi = 0; mi < k1; mi++)
+            for (int j = 0; j < decomp_length; j++) {
+                const u64 a = ff_canon(tr[((b * k1 + mi) * decomp_length + j) * NTT_N + x]);
+                const u64 w = ff_canon(bk_row[(((size_t)mi * decomp_length + j) * k1 + mo) * NTT_N + x]);
+                acc = ff_add(acc, ff_canon(ff_mul_prepared(a, w)));
+            }
+        out[i] = ff_canon(acc);
+    }
+}
+
 // tlwe_add_to (tlwe.py:173-175): wrap-around int32 addition, float addition of the variances
 __global__ void add_to_kernel(i32 *__restrict__ res, const i32 *__restrict__ src, size_t n, float *__restrict__ res_cv,
                               const float *__restrict__ src_cv, size_t n_cv)

@@ -234,6 +234,24 @@ class Engine:
         self._call('nb_tlwe_add_to', _ptr(res), _ptr(src), res.numel(), _ptr(res_cv), _ptr(src_cv),
                    0 if res_cv is None else res_cv.numel())
 
+    def tgsw_decompose(self, acc, decomp_length, bs_log2_base, offset):
+        """acc (..., N) int32 -> (..., l, N) digits (nb_tgsw_decompose)."""
+        acc = self._dense(acc, torch.int32)
+        n_poly = acc.shape[-1]
+        out = self.empty(tuple(acc.shape[:-1]) + (decomp_length, n_poly), torch.int32)
+        self._call('nb_tgsw_decompose', _ptr(out), _ptr(acc), acc.numel() // n_poly, decomp_length, bs_log2_base,
+                   int(offset), n_poly.bit_length() - 1)
+        return out
+
+    def tgsw_mac(self, tr, bk_row, mask_size, decomp_length):
+        """tr (B, k+1, l, 1024) u64, bk_row (k+1, l, k+1, 1024) u64 (reference layout) -> (B, k+1, 1024) u64."""
+        tr = self._dense(tr, torch.int64)
+        bk_row = self._dense(bk_row, torch.int64)
+        batch = tr.numel() // ((mask_size + 1) * decomp_length * N)
+        out = self.empty((batch, mask_size + 1, N), torch.int64)
+        self._call('nb_tgsw_mac', _ptr(out), _ptr(tr), _ptr(bk_row), batch, mask_size, decomp_length)
+        return out
+
     def t32_to_phase(self, out, messages, mspace_size):
         assert out.is_contiguous() and out.dtype == torch.int32
         messages = self._dense(messages, torch.int32)

@@ -72,7 +72,7 @@ _BINARY_GATES = {
 def _binary_gate(name, thr, cloud_key, result, a, b, perf_params):
     check_shape(result, a, b)
     num, den, sa, sb = _BINARY_GATES[name]
-    if not _single_kernel(perf_params):
+    if not _single_kernel(perf_params, cloud_key.bootstrap_key):
         # the reference's own sequence (gates.py:108-121): trivial constant, two linear updates, bootstrap
         bk = cloud_key.bootstrap_key
         temp = LweSampleArray.empty(thr, bk.in_out_params, result.shape)
@@ -150,7 +150,7 @@ def gate_mux(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, b: LweSa
     bk, ks = cloud_key.bootstrap_key, cloud_key.keyswitch_key
     and_const = phase_to_t32(-1, 8)
     shape = tuple(result.shape)
-    if not _single_kernel(perf_params):
+    if not _single_kernel(perf_params, bk):
         # the reference's own sequence (gates.py:629-664)
         in_out, extracted = bk.in_out_params, bk.extract_params
         temp = LweSampleArray.empty(thr, in_out, shape)

@@ -43,6 +43,12 @@ class PerformanceParameters:
         return self.__class__ == other.__class__ and self._key() == other._key()
 
 
+def single_kernel_bootstrap_supported(nufhe_params, device_params=None):
+    """blind_rotate.py:37-86: the fused kernel exists for mask size 1 and the default decomposition only."""
+    from .tgsw import fused_kernel_supported
+    return fused_kernel_supported(nufhe_params.tgsw_params)
+
+
 class PerformanceParametersForDevice:
     """performance.py:137-236.  `single_kernel_bootstrap` defaults to True (the fused kernel); False selects the
     reference's multi-kernel sequence of separate launches (bootstrap.py:96-196), same results, much slower."""
@@ -55,7 +61,13 @@ class PerformanceParametersForDevice:
         self.use_constant_memory_multi_iter = False
         self.use_constant_memory_single_iter = False
         self.transforms_per_block = 4
-        self.single_kernel_bootstrap = perf_params.single_kernel_bootstrap is not False
+        supported = single_kernel_bootstrap_supported(perf_params.nufhe_params, device_params)
+        if perf_params.single_kernel_bootstrap is None:
+            self.single_kernel_bootstrap = supported
+        else:
+            if perf_params.single_kernel_bootstrap and not supported:           # performance.py:183-185
+                raise ValueError("Single kernel bootstrap is not supported for this parameter set")
+            self.single_kernel_bootstrap = bool(perf_params.single_kernel_bootstrap)
         self.low_end_device = False
 
     def _key(self):

@@ -119,11 +119,37 @@ def tgsw_encrypt_int(thr, rng, result: TGswSampleArray, messages, noise: float, 
     tgsw_add_message(thr, result, messages)
 
 
+def fused_kernel_supported(params: TGswParams):
+    """The parameter set of the fused bootstrap kernel (the reference's single-kernel path has the same limits,
+    blind_rotate.py:37-86)."""
+    return (params.tlwe_params.mask_size == 1 and params.decomp_length == 2 and params.bs_log2_base == 10
+            and params.tlwe_params.polynomial_degree == 1024)
+
+
+def tgsw_transformed_external_mul_steps(thr, result: TLweSampleArray, bootstrap_key, bk_row_idx: int):
+    """The external product as the reference's computation composes it (tgsw_gpu.py:110-169): gadget decomposition,
+    forward transforms, multiply-accumulate with the key row in the reference's own layout, inverse transforms.
+    Works for any TLWE mask size k and decomposition length."""
+    params = bootstrap_key.params
+    k, l = params.tlwe_params.mask_size, params.decomp_length
+    coeffs = result.a.coeffs
+    dec = thr.tgsw_decompose(coeffs, l, params.bs_log2_base, params.offset)          # (..., k+1, l, N)
+    tr = thr.ntt_forward_i32(dec)
+    row = bootstrap_key.samples.a.coeffs[bk_row_idx]                                 # (k+1, l, k+1, N)
+    mac = thr.tgsw_mac(tr, row, k, l)
+    res = thr.ntt_inverse_i32(mac)
+    coeffs.copy_(res.reshape(coeffs.shape))
+
+
 def tgsw_transformed_external_mul(thr, result: TLweSampleArray, bootstrap_key, bk_row_idx: int, perf_params=None):
     """tgsw.py:165-172: result <- bootstrap_key[bk_row_idx] (x) result.
-    `bootstrap_key` is a BootstrapKey-owned TransformedTGswSampleArray; the engine-format copy of the
-    key is built once and cached on it."""
+    `bootstrap_key` is a BootstrapKey-owned TransformedTGswSampleArray.  For the default parameters (k = 1, l = 2)
+    this is one launch of the fused kernel's step on the engine-format copy of the key (built once, cached); any
+    other mask size / decomposition goes through the separate steps above."""
     assert len(bootstrap_key.shape) == 1
+    if not fused_kernel_supported(bootstrap_key.params):
+        tgsw_transformed_external_mul_steps(thr, result, bootstrap_key, bk_row_idx)
+        return
     bk_int = engine_format(thr, bootstrap_key)
     coeffs = result.a.coeffs
     if coeffs.is_contiguous():
@@ -136,11 +162,10 @@ def tgsw_transformed_external_mul(thr, result: TLweSampleArray, bootstrap_key, b
 
 def engine_format(thr, tgsw: TransformedTGswSampleArray):
     """The bootstrap key re-laid for the MAC stage of the fused kernel (nb_bk_prepare), cached."""
-    params = tgsw.params
-    if (params.tlwe_params.mask_size != 1 or params.decomp_length != 2 or params.bs_log2_base != 10
-            or params.tlwe_params.polynomial_degree != 1024):
-        raise ValueError("The B200 bootstrap kernel supports mask_size=1, decomp_length=2, "
-                         "bs_log2_base=10, polynomial_degree=1024 only")
+    if not fused_kernel_supported(tgsw.params):
+        raise ValueError("The fused B200 bootstrap kernel supports mask_size=1, decomp_length=2, bs_log2_base=10, "
+                         "polynomial_degree=1024 only; other parameters run on the multi-kernel path "
+                         "(single_kernel_bootstrap=False)")
     cached = getattr(tgsw, '_engine_format', None)
     if cached is None or cached.device != tgsw.samples.a.coeffs.device:
         cached = thr.bk_prepare(tgsw.samples.a.coeffs)

@@ -250,6 +250,47 @@ def test_bootstrap_seams(ctx, key_pair, okeys, nufhe):
     assert (host(accum.a.coeffs) == O.blind_rotate(acc0, okeys.bk[:3], numpy.ascontiguousarray(bara[:, :3]))).all()
 
 
+def _sha(t, unsigned=False):
+    import hashlib
+    return hashlib.sha256(numpy.ascontiguousarray(host(t, unsigned)).tobytes()).hexdigest()
+
+
+def test_mask_size_2_against_reference_golden(nufhe, golden):
+    """`NuFHEParameters(tlwe_mask_size=2)`: keys from the seed must equal the reference's (digests in
+    tests/golden/k2.npz, produced by the reference's closures), and gate_nand on the golden ciphertexts must return
+    the reference's bits -- 500 CMux steps of the multi-kernel path with 3 accumulator polynomials."""
+    g = golden('k2')
+    ctx = nufhe.Context(rng=nufhe.DeterministicRNG(int(g['seed'])))
+    sk, ck = ctx.make_key_pair(tlwe_mask_size=2)
+    assert ck.params == nufhe.NuFHEParameters(tlwe_mask_size=2)
+    bk = ck.bootstrap_key.tgsw.samples.a.coeffs
+    assert tuple(bk.shape) == (500, 3, 2, 3, 1024)
+    assert _sha(sk.lwe_key.key) == str(g['lwe_key_sha'])
+    assert (host(bk[0], True) == g['bk_row0']).all() and (host(bk[499], True) == g['bk_row499']).all()
+    assert _sha(bk, True) == str(g['bk_sha'])
+    ks = ck.keyswitch_key.lwe
+    assert tuple(ks.a.shape) == (2048, 8, 4, 500)
+    assert _sha(ks.a) == str(g['ks_a_sha']) and _sha(ks.b) == str(g['ks_b_sha'])
+    c1, c2 = ctx.encrypt(sk, G.GATE_BITS_A[:2]), ctx.encrypt(sk, G.GATE_BITS_B[:2])
+    assert (host(c1.a) == g['c1_a']).all() and (host(c1.b) == g['c1_b']).all()
+    assert (host(c2.a) == g['c2_a']).all() and (host(c2.b) == g['c2_b']).all()
+    vm = ctx.make_virtual_machine(ck)
+    assert not vm.perf_params.single_kernel_bootstrap
+    r = vm.gate_nand(c1, c2)
+    assert (host(r.a) == g['nand_a']).all() and (host(r.b) == g['nand_b']).all()
+    assert (ctx.decrypt(sk, r) == g['nand_bits']).all()
+    with pytest.raises(ValueError):
+        ctx.make_virtual_machine(ck, perf_params=nufhe.PerformanceParameters(ck.params, single_kernel_bootstrap=True))
+    # the other gates decrypt to their truth tables; serialization keeps the parameters
+    a = numpy.array([True, True, False, False])
+    b = numpy.array([True, False, True, False])
+    ca, cb = ctx.encrypt(sk, a), ctx.encrypt(sk, b)
+    assert (ctx.decrypt(sk, vm.gate_xor(ca, cb)) == (a ^ b)).all()
+    assert (ctx.decrypt(sk, vm.gate_mux(ca, cb, vm.gate_not(cb))) == numpy.where(a, b, ~b)).all()
+    ck2 = ctx.load_cloud_key(ck.dumps())
+    assert ck2 == ck and ck2.params == ck.params
+
+
 def test_find_devices(nufhe):
     devs = nufhe.find_devices()
     assert len(devs) >= 1 and devs[0].api_name == 'CUDA'

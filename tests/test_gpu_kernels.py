@@ -262,3 +262,32 @@ def test_transform_interface(eng):
         t2(out, dev_u64(eng, ff[:2]))
     with pytest.raises(ValueError):
         get_transform('FFT')
+
+
+def test_external_product_steps_golden(eng, golden):
+    """The external product as separate steps (decompose, forward transforms, MAC on the reference's key layout,
+    inverse transforms) against the reference's closures: k = 1 (tests/golden/tgsw.npz) and k = 2
+    (tests/golden/k2_small.npz, make_golden_k2.py)."""
+    g = golden('tgsw')
+    accum_small, accum_full, tr_sample, bk = G.tgsw_inputs()
+    offset = -2145386496                                                 # TGswParams.offset, SURVEY 8 a8
+    dec = eng.tgsw_decompose(eng.to_device(accum_full), 2, 10, offset)
+    assert (eng.to_host(dec) == g['decomp']).all()
+    mac = eng.tgsw_mac(dev_u64(eng, tr_sample), dev_u64(eng, bk[1]), 1, 2)
+    assert (eng.to_host(mac, True) == g['mac']).all()
+    for acc, row, key in ((accum_small, 2, 'ext_small'), (accum_full, 0, 'ext_full')):
+        d = eng.tgsw_decompose(eng.to_device(acc), 2, 10, offset)
+        res = eng.ntt_inverse_i32(eng.tgsw_mac(eng.ntt_forward_i32(d), dev_u64(eng, bk[row]), 1, 2))
+        assert (eng.to_host(res) == g[key]).all(), key
+    # k = 2
+    g2 = golden('k2_small')
+    rng = G.rs(205)
+    accum = G.torus32(rng, (2, 3, 1024))
+    tr2 = G.ff_numbers(rng, (2, 3, 2, 1024))
+    bk2 = G.ff_numbers(rng, (2, 3, 2, 3, 1024))
+    dec = eng.tgsw_decompose(eng.to_device(accum), 2, 10, offset)
+    assert (eng.to_host(dec) == g2['decomp']).all()
+    mac = eng.tgsw_mac(dev_u64(eng, tr2), dev_u64(eng, bk2[1]), 2, 2)
+    assert (eng.to_host(mac, True) == g2['mac']).all()
+    res = eng.ntt_inverse_i32(eng.tgsw_mac(eng.ntt_forward_i32(dec), dev_u64(eng, bk2[0]), 2, 2))
+    assert (eng.to_host(res) == g2['ext']).all()

@@ -62,10 +62,19 @@ def test_parameters_and_shapes():
     assert p.ks_decomp_length == 8 and p.ks_log2_base == 2
     with pytest.raises(ValueError):
         nufhe.NuFHEParameters(transform_type='FFT')
-    with pytest.raises(ValueError):
-        nufhe.NuFHEParameters(tlwe_mask_size=2)
     with pytest.raises(AssertionError):
         nufhe.NuFHEParameters(transform_type='DCT')
+    # mask size 2 exists on the multi-kernel path only, like in the reference (blind_rotate.py:53-58, performance.py:183-185)
+    p2 = nufhe.NuFHEParameters(tlwe_mask_size=2)
+    assert p2 != p and p2.tgsw_params.tlwe_params.extracted_lweparams.size == 2048
+
+    class Dev:
+        pass
+    assert nufhe.PerformanceParameters(p).for_device(Dev()).single_kernel_bootstrap
+    assert not nufhe.PerformanceParameters(p2).for_device(Dev()).single_kernel_bootstrap
+    assert not nufhe.PerformanceParameters(p, single_kernel_bootstrap=False).for_device(Dev()).single_kernel_bootstrap
+    with pytest.raises(ValueError):
+        nufhe.PerformanceParameters(p2, single_kernel_bootstrap=True).for_device(Dev())
     pp = nufhe.PerformanceParameters(p, single_kernel_bootstrap=True)
     assert pp == nufhe.PerformanceParameters(p, single_kernel_bootstrap=True)
     assert pp != nufhe.PerformanceParameters(p)
