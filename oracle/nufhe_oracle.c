@@ -362,6 +362,60 @@ void orc_tgsw_external_mul(i32 *accum, const u64 *bk, size_t bk_row, size_t batc
     for (size_t b = 0; b < batch; b++) external_mul_one(accum + b * 2 * NPOLY, row);
 }
 
+/* The same three steps for any TLWE mask size k (k1 = k + 1 accumulator polynomials), decomposition length 2:
+ * what `NuFHEParameters(tlwe_mask_size=2)` runs (tgsw_cpu.py:26-106 are written for general k).
+ * decomposition: result (polys, 2, N) from sample (polys, N) */
+void orc_tgsw_decompose_polys(i32 *result, const i32 *sample, size_t polys)
+{
+    for (size_t p = 0; p < polys; p++)
+        for (int x = 0; x < NPOLY; x++)
+            decompose_coeff(sample[p * NPOLY + x], &result[(p * 2 + 0) * NPOLY + x], &result[(p * 2 + 1) * NPOLY + x]);
+}
+/* res (B, k1, N) = sum_{mi,j} mul_prepared(tr (B, k1, 2, N), bk_row (k1, 2, k1, N)) */
+static void mac_one_k(u64 *res, const u64 *tr, const u64 *bk_row, int k1)
+{
+    for (int mo = 0; mo < k1; mo++)
+        for (int x = 0; x < NPOLY; x++) {
+            u64 acc = 0;
+            for (int mi = 0; mi < k1; mi++)
+                for (int j = 0; j < 2; j++)
+                    acc = ff_add(acc, ff_mul_prepared(tr[(mi * 2 + j) * NPOLY + x],
+                                                      bk_row[((mi * 2 + j) * k1 + mo) * NPOLY + x]));
+            res[mo * NPOLY + x] = acc;
+        }
+}
+void orc_tgsw_mac_k(u64 *res, const u64 *tr, const u64 *bk_row, size_t batch, int k1)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t b = 0; b < batch; b++) mac_one_k(res + b * k1 * NPOLY, tr + b * k1 * 2 * NPOLY, bk_row, k1);
+}
+/* accum (B, k1, N) <- bk_row (x) accum */
+void orc_tgsw_external_mul_k(i32 *accum, const u64 *bk_row, size_t batch, int k1)
+{
+    init_tables();
+#pragma omp parallel for schedule(static)
+    for (size_t b = 0; b < batch; b++) {
+        i32 *acc = accum + b * k1 * NPOLY;
+        u64 tr[8 * 2 * NPOLY] = {0}, mac[8 * NPOLY], d0[NPOLY], d1[NPOLY], res[NPOLY];   /* k1 <= 8 */
+        for (int m = 0; m < k1; m++) {
+            for (int x = 0; x < NPOLY; x++) {
+                i32 a, c;
+                decompose_coeff(acc[m * NPOLY + x], &a, &c);
+                d0[x] = ff_from_i32(a);
+                d1[x] = ff_from_i32(c);
+            }
+            ntt_forward_ff(tr + (m * 2 + 0) * NPOLY, d0);
+            ntt_forward_ff(tr + (m * 2 + 1) * NPOLY, d1);
+        }
+        mac_one_k(mac, tr, bk_row, k1);
+        for (int mo = 0; mo < k1; mo++) {
+            memcpy(d0, mac + mo * NPOLY, sizeof(d0));
+            ntt_inverse_ff(res, d0);
+            for (int x = 0; x < NPOLY; x++) acc[mo * NPOLY + x] = ff_to_i32(res[x]);
+        }
+    }
+}
+
 /* mux_rotate, bootstrap.py:96-109: ACC <- ACC + BK_i (x) ((X^bara_i - 1) ACC), one ciphertext */
 static void mux_rotate_one(i32 *acc /*2,N*/, const u64 *bk_row, int barai)
 {

@@ -209,6 +209,35 @@ def tgsw_external_mul(accum, bk, bk_row):
     return out
 
 
+def tgsw_decompose_k(sample):
+    """Gadget decomposition of (..., N) polynomials -> (..., 2, N), any number of polynomials per sample."""
+    sample = _c(sample, numpy.int32)
+    out = numpy.empty(sample.shape[:-1] + (2, N), numpy.int32)
+    lib().orc_tgsw_decompose_polys(_p(out), _p(sample), _sz(sample.size // N))
+    return out
+
+
+def tgsw_mac_k(tr, bk_row):
+    """tr (B, k+1, 2, N), bk_row (k+1, 2, k+1, N) -> (B, k+1, N), any mask size k."""
+    tr = _c(tr, numpy.uint64)
+    bk_row = _c(bk_row, numpy.uint64)
+    k1 = bk_row.shape[0]
+    B = tr.size // (k1 * 2 * N)
+    out = numpy.empty((B, k1, N), numpy.uint64)
+    lib().orc_tgsw_mac_k(_p(out), _p(tr), _p(bk_row), _sz(B), ctypes.c_int(k1))
+    return out
+
+
+def tgsw_external_mul_k(accum, bk_row):
+    """Returns bk_row (x) accum for accum (B, k+1, N) and bk_row (k+1, 2, k+1, N), any mask size k <= 7."""
+    out = _c(accum, numpy.int32).copy()
+    bk_row = _c(bk_row, numpy.uint64)
+    k1 = bk_row.shape[0]
+    assert k1 <= 8 and out.shape[-2] == k1
+    lib().orc_tgsw_external_mul_k(_p(out), _p(bk_row), _sz(out.size // (k1 * N)), ctypes.c_int(k1))
+    return out
+
+
 def blind_rotate(acc, bk, bara):
     out = _c(acc, numpy.int32).copy()
     bk = _c(bk, numpy.uint64)

@@ -291,3 +291,16 @@ def test_external_product_steps_golden(eng, golden):
     assert (eng.to_host(mac, True) == g2['mac']).all()
     res = eng.ntt_inverse_i32(eng.tgsw_mac(eng.ntt_forward_i32(dec), dev_u64(eng, bk2[0]), 2, 2))
     assert (eng.to_host(res) == g2['ext']).all()
+
+
+@pytest.mark.parametrize('k,batch', [(1, 5), (2, 7), (3, 2)])
+def test_external_product_steps_vs_oracle(eng, k, batch):
+    rng = G.rs(600 + k)
+    accum = G.torus32(rng, (batch, k + 1, 1024))
+    bk_row = G.ff_numbers(rng, (k + 1, 2, k + 1, 1024))
+    dec = eng.tgsw_decompose(eng.to_device(accum), 2, 10, -2145386496)
+    assert (eng.to_host(dec) == O.tgsw_decompose_k(accum)).all()
+    tr = eng.ntt_forward_i32(dec)
+    mac = eng.tgsw_mac(tr, dev_u64(eng, bk_row), k, 2)
+    assert (eng.to_host(mac, True) == O.tgsw_mac_k(eng.to_host(tr, True), bk_row)).all()
+    assert (eng.to_host(eng.ntt_inverse_i32(mac)) == O.tgsw_external_mul_k(accum, bk_row)).all()

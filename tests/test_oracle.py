@@ -133,3 +133,21 @@ def test_all_gates_truth_tables(keys):
     for name, want in truth.items():
         assert (keys.decrypt(O.gate_binary(name, a, b, keys.bk, keys.ks)) == want).all(), name
     assert (keys.decrypt(O.gate_mux(a, b, c, keys.bk, keys.ks)) == numpy.where(a_bits, b_bits, c_bits)).all()
+
+
+def test_mask_size_2_steps(golden):
+    """The general-k restatement of decomposition / MAC / external product against the reference's closures run with
+    `NuFHEParameters(tlwe_mask_size=2)` (tests/golden/make_golden_k2.py), and against the k = 1 goldens."""
+    g = golden('k2_small')
+    rng = G.rs(205)
+    accum = G.torus32(rng, (2, 3, 1024))
+    tr = G.ff_numbers(rng, (2, 3, 2, 1024))
+    bk = G.ff_numbers(rng, (2, 3, 2, 3, 1024))
+    assert (O.tgsw_decompose_k(accum) == g['decomp']).all()
+    assert (O.tgsw_mac_k(tr, bk[1]) == g['mac']).all()
+    assert (O.tgsw_external_mul_k(accum, bk[0]) == g['ext']).all()
+    g1 = golden('tgsw')
+    accum_small, accum_full, tr_sample, bk1 = G.tgsw_inputs()
+    assert (O.tgsw_decompose_k(accum_full) == g1['decomp']).all()
+    assert (O.tgsw_mac_k(tr_sample, bk1[1]) == g1['mac']).all()
+    assert (O.tgsw_external_mul_k(accum_full, bk1[0]) == g1['ext_full']).all()
