@@ -143,9 +143,10 @@ class VirtualMachine:
         self.params = cloud_key.params
         self.cloud_key = cloud_key
         self.perf_params = perf_params
-        # lay the bootstrap key out for the engine once, at VM creation rather than at the first gate
-        from .tgsw import engine_format
-        engine_format(thread, cloud_key.bootstrap_key.tgsw)
+        # lay the bootstrap key out for the fused kernel once, at VM creation rather than at the first gate
+        from .tgsw import engine_format, fused_kernel_supported
+        if perf_params.single_kernel_bootstrap and fused_kernel_supported(cloud_key.bootstrap_key.bk_params):
+            engine_format(thread, cloud_key.bootstrap_key.tgsw)
 
     def empty_ciphertext(self, shape):
         return empty_ciphertext(self.thread, self.params, shape)
