@@ -19,17 +19,6 @@
 #define NB_D inline
 #endif
 
-// NB_LOCKSTEP(): keeps the warps of a CTA within one instruction-cache window of each other.
-// The transform code is fully unrolled straight-line code far larger than the SM's instruction
-// cache; warps that drift apart each stream it from L2 on their own ("no instruction" stalls were
-// the top stall reason in the first ncu capture, profiles/r1_v1_*).  A cheap CTA barrier every few
-// hundred instructions makes one fetch serve all warps.
-#if defined(__CUDA_ARCH__) && defined(NB_LOCKSTEP_ON)
-#define NB_LOCKSTEP() __syncthreads()
-#else
-#define NB_LOCKSTEP() ((void)0)
-#endif
-
 namespace nb {
 
 typedef uint64_t u64;
@@ -236,12 +225,6 @@ NB_HD u64 ff_mul(u64 a, u64 b)
     unsigned __int128 pr = (unsigned __int128)a * b;
     return ff_reduce128((u64)pr, (u64)(pr >> 64));
 #endif
-}
-
-// a*b + c*d mod p with a single reduction of the 129-bit sum
-NB_HD u64 ff_mul2_add(u64 a, u64 b, u64 c, u64 d)
-{
-    return ff_add(ff_mul(a, b), ff_mul(c, d));
 }
 
 // a0*b0 + a1*b1 + a2*b2 + a3*b3 mod p: the four 128-bit products are summed first (130 bits) and

@@ -1,16 +1,16 @@
 // kernels.cuh -- sm_100a kernels of the TFHE gate-bootstrapping hot path.
 //
-// Work decomposition: ONE WARP PER POLYNOMIAL.  A ciphertext's accumulator (k+1 = 2 polynomials of
-// 1024 Torus32 coefficients) is owned by a pair of warps; warp `mi` owns ACC[mi] in shared memory,
-// transforms the two gadget digits of its polynomial, multiplies them with its half of the
-// bootstrap-key row, swaps one partial product with its partner through shared memory, and runs the
-// inverse transform of output polynomial `mi`.  The only block-level synchronisation on the path is
-// a 64-thread named barrier around that swap.
+// Work decomposition of the fused bootstrap: a CTA owns one or two ciphertexts whose accumulators and work
+// polynomials live in shared memory; every CMux step is seven CTA-wide phases (br_phases.cuh) separated by
+// __syncthreads, 16 field elements per thread and phase.  The stand-alone transforms reuse the same phases.
+// The key switch is a TMA-fed producer / consumer pipeline.  The small kernels at the end are the separate steps of
+// the reference's multi-kernel bootstrap.
 //
 // Reference counterparts: nufhe/blind_rotate.mako:18-226 (fused bootstrap), tgsw_gpu.py:110-169
 // (external product), transform/computation.mako:18-143 (stand-alone transform), lwe_gpu.mako:59-118
 // (key switch).  Nothing here is derived from those kernels' structure (128 threads/transform,
-// 8*2*8*8 radix plan, 15 block barriers per step); see ntt_lane.cuh for the transform we use.
+// 8*2*8*8 radix plan, 15 block barriers per step); see ntt_lane.cuh for the transform we use and DESIGN.md
+// section 4 for the measurements behind each choice.
 #pragma once
 #include <cuda_runtime.h>
 #include "ntt_lane.cuh"

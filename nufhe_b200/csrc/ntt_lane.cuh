@@ -42,7 +42,6 @@ template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dif_inlane
             v[i0] = ff_add(a, b);
             v[i1] = ff_shl<(ROOTLOG * k * (1 << s)) % 192>(ff_sub(a, b));
         });
-        NB_LOCKSTEP();
     });
 }
 
@@ -70,7 +69,6 @@ template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dit_inlane
                 v[i1] = ff_sub(a, t);
             }
         });
-        NB_LOCKSTEP();
     });
 }
 
