@@ -349,6 +349,22 @@ NB_HD void phase_fwd1_generic(int task, const u64 *x /* 16 values, x[j1] = in[64
         w[r * ROW_STRIDE] = ff_mul(v[r], twd[r * 64 + j2]);
     });
 }
+// first pass with Torus32 inputs (i32_conversion): the conversion and the twist are one step (ff_twist_i32)
+NB_HD void phase_fwd1_i32(int task, const i32 *x /* 16 values, x[j1] = in[64 j1 + j2] */, u64 *w_all, const u64 *twd)
+{
+    const int j2 = task & 63, p = task >> 6;
+    u64 v[16];
+    static_for<0, 16>([&](auto J) {
+        constexpr int j1 = decltype(J)::value;
+        v[j1] = ff_twist_i32<j1>(x[j1]);
+    });
+    dif_inlane<4, 12, 0>(v);
+    u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        w[r * ROW_STRIDE] = ff_mul(v[r], twd[r * 64 + j2]);
+    });
+}
 // last inverse pass with generic outputs: y[j1] = out[64 j1 + j2], almost-canonical ([0, p])
 NB_HD void phase_inv1_generic(int task, u64 *y, const u64 *w_all, const u64 *twd_inv)
 {
@@ -363,6 +379,25 @@ NB_HD void phase_inv1_generic(int task, u64 *y, const u64 *w_all, const u64 *twd
     static_for<0, 16>([&](auto J) {
         constexpr int j1 = decltype(J)::value;
         y[j1] = ff_shl<(192 - 6 * j1) % 192>(v[j1]);
+    });
+}
+
+// last inverse pass with Torus32 outputs: 2^(-6 j1) = -2^(96 - 6 j1) for j1 >= 1 (the centred lift is odd), like
+// the fused kernel's inv1
+NB_HD void phase_inv1_i32(int task, i32 *y, const u64 *w_all, const u64 *twd_inv)
+{
+    const int j2 = task & 63, p = task >> 6;
+    const u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
+    u64 v[16];
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        v[r] = ff_mul(w[r * ROW_STRIDE], twd_inv[r * 64 + j2]);
+    });
+    dit_inlane<4, 12, 0>(v);
+    y[0] = ff_to_i32(v[0]);
+    static_for<1, 16>([&](auto J) {
+        constexpr int j1 = decltype(J)::value;
+        y[j1] = (i32)(0u - (u32)ff_to_i32(ff_shl<96 - 6 * j1>(v[j1])));
     });
 }
 

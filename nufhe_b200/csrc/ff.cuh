@@ -268,6 +268,34 @@ template <int J1> NB_HD u64 ff_twist_small(u32 u)
     }
 }
 
+// x * 2^(6 J1) for a Torus32 coefficient x (any int32): the twist of the stand-alone forward transform with
+// i32_conversion (ntt.mako:395-399 followed by the first shift of the transform).  |x| <= 2^31 has two limbs after
+// the bit shift, so the three limb combinations collapse to at most one modular subtraction.  Result in [0, p].
+template <int J1> NB_HD u64 ff_twist_i32(i32 x)
+{
+    constexpr int s = 6 * J1, q = s / 32, r = s % 32;
+    static_assert(s < 96, "twist exponent");
+    const bool neg = x < 0;
+    const u32 m = neg ? 0u - (u32)x : (u32)x;
+    u64 v;
+    if constexpr (q == 0) {
+        v = (u64)m << s;                                              // < 2^62
+    } else {
+        const u32 y0 = m << r, y1 = r ? m >> (32 - r) : 0u;           // |x| * 2^r = y0 + y1 phi
+        if constexpr (q == 1) {                                       // (y0 + y1) phi - y1, carry of y0 + y1 folded as eps
+            const u64 t = (u64)y0 + y1;
+            v = ff_sub((t << 32) + (t >> 32) * FF_EPS, (u64)y1);
+        } else {                                                      // y0 phi^2 + y1 phi^3 = y0 eps - y1
+            v = ff_sub(ff_eps_mul(y0), (u64)y1);
+        }
+    }
+#if defined(__CUDA_ARCH__)
+    return neg ? FF_P - v : v;                                        // p may stand for 0 on the device
+#else
+    return neg ? ff_neg(v) : v;
+#endif
+}
+
 // a * b * 2^-64 mod p, the reference's Montgomery product (arithmetic.mako:355-419 `mul_prepared`)
 constexpr u64 FF_RINV = 0xfffffffe00000001ULL;     // 2^-64 mod p (polynomial_transform_ntt.py:66)
 NB_HD u64 ff_mul_prepared(u64 a, u64 b) { return ff_mul(ff_mul(a, b), FF_RINV); }

@@ -44,6 +44,39 @@ void emul_ntt_inverse(const u64 *in, u64 *out, size_t batch)
     }
 }
 
+// the same with Torus32 on the natural-order side (i32_conversion): forward reads int32, inverse writes int32
+void emul_ntt_forward_i32(const i32 *in, u64 *out, size_t batch)
+{
+    static PhaseTables T;
+    std::vector<u64> w(NTT_SWEEP_POLYS * POLY_STRIDE);
+    for (size_t b = 0; b < batch; b++) {
+        for (int task = 0; task < 64; task++) {
+            i32 x[16];
+            for (int j1 = 0; j1 < 16; j1++) x[j1] = in[b * NTT_N + 64 * j1 + task];
+            phase_fwd1_i32(task, x, w.data(), T.fwd.data());
+        }
+        for (int row = 0; row < 16; row++) for (int g = 0; g < 4; g++) phase_fwd2(0, row, g, w.data());
+        for (int row = 0; row < 16; row++) for (int u = 0; u < 4; u++) phase_fwd3(0, row, u, w.data());
+        for (int k = 0; k < NTT_N; k++) out[b * NTT_N + k] = ff_canon(w[w_position_of_natural(k)]);
+    }
+}
+
+void emul_ntt_inverse_i32(const u64 *in, i32 *out, size_t batch)
+{
+    static PhaseTables T;
+    std::vector<u64> w(NTT_SWEEP_POLYS * POLY_STRIDE);
+    for (size_t b = 0; b < batch; b++) {
+        for (int k = 0; k < NTT_N; k++) w[w_position_of_natural(k)] = ff_canon(in[b * NTT_N + k]);
+        for (int row = 0; row < 16; row++) for (int u = 0; u < 4; u++) phase_inv3(0, row, u, w.data());
+        for (int row = 0; row < 16; row++) for (int g = 0; g < 4; g++) phase_inv2(0, row, g, w.data());
+        for (int task = 0; task < 64; task++) {
+            i32 y[16];
+            phase_inv1_i32(task, y, w.data(), T.inv.data());
+            for (int j1 = 0; j1 < 16; j1++) out[b * NTT_N + 64 * j1 + task] = y[j1];
+        }
+    }
+}
+
 // One external-product step of the phase-structured kernel (br_phases.cuh) for up to BR2_CT
 // ciphertexts, phases executed in order with all "threads" of a phase run back to back.
 // acc: (nct, 2, 1024) in/out; bk_ref_row: reference layout (2,2,2,1024) Montgomery; rot: rotation

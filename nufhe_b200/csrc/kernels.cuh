@@ -39,13 +39,17 @@ __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_forward_kernel(const
         {   // pass 1: thread = (poly, j2), reads x[64 j1 + j2]
             const int pl = tid >> 6, j2 = tid & 63;
             const size_t p = min(p0 + pl, batch - 1);
-            u64 x[16];
+            if (IN_I32) {
+                i32 x[16];
 #pragma unroll
-            for (int j1 = 0; j1 < 16; j1++) {
-                const size_t idx = p * NTT_N + 64 * j1 + j2;
-                x[j1] = IN_I32 ? ff_from_i32(((const i32 *)in)[idx]) : ff_canon(((const u64 *)in)[idx]);
+                for (int j1 = 0; j1 < 16; j1++) x[j1] = ((const i32 *)in)[p * NTT_N + 64 * j1 + j2];
+                phase_fwd1_i32(tid, x, w, twd);
+            } else {
+                u64 x[16];
+#pragma unroll
+                for (int j1 = 0; j1 < 16; j1++) x[j1] = ff_canon(((const u64 *)in)[p * NTT_N + 64 * j1 + j2]);
+                phase_fwd1_generic(tid, x, w, twd);
             }
-            phase_fwd1_generic(tid, x, w, twd);
         }
         __syncthreads();
         { const int g = tid >> 6, x = tid & 63; phase_fwd2(x >> 4, x & 15, g, w); }
@@ -94,14 +98,19 @@ __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_inverse_kernel(const
         __syncthreads();
         {
             const int pl = tid >> 6, j2 = tid & 63;
-            u64 y[16];
-            phase_inv1_generic(tid, y, w, twd);
-            if (p0 + pl < batch) {
+            if (OUT_I32) {
+                i32 y[16];
+                phase_inv1_i32(tid, y, w, twd);
+                if (p0 + pl < batch) {
 #pragma unroll
-                for (int j1 = 0; j1 < 16; j1++) {
-                    const size_t idx = (p0 + pl) * NTT_N + 64 * j1 + j2;
-                    if (OUT_I32) ((i32 *)out)[idx] = ff_to_i32(ff_canon(y[j1]));
-                    else ((u64 *)out)[idx] = ff_canon(y[j1]);
+                    for (int j1 = 0; j1 < 16; j1++) ((i32 *)out)[(p0 + pl) * NTT_N + 64 * j1 + j2] = y[j1];
+                }
+            } else {
+                u64 y[16];
+                phase_inv1_generic(tid, y, w, twd);
+                if (p0 + pl < batch) {
+#pragma unroll
+                    for (int j1 = 0; j1 < 16; j1++) ((u64 *)out)[(p0 + pl) * NTT_N + 64 * j1 + j2] = ff_canon(y[j1]);
                 }
             }
         }

@@ -154,6 +154,35 @@ def test_lane_ntt_matches_reference_golden(emul, golden):
     assert (out == g['inv_u64']).all()
 
 
+def test_lane_ntt_i32_conversion(emul, golden):
+    """The stand-alone transforms with Torus32 on the natural-order side: the forward pass fuses the conversion with
+    the twist (ff_twist_i32), the inverse negates after the conversion.  Edge coefficients (0, +-1, +-2^31) and
+    random ones against the reference's goldens and the oracle."""
+    g = golden('ntt')
+    x_i32, x_u64 = G.ntt_inputs()
+    out = numpy.empty(x_i32.shape, numpy.uint64)
+    emul.emul_ntt_forward_i32(_p(x_i32), _p(out), ctypes.c_size_t(x_i32.shape[0]))
+    assert (out == g['fwd_i32']).all()
+    back = numpy.empty(x_u64.shape, numpy.int32)
+    emul.emul_ntt_inverse_i32(_p(x_u64), _p(back), ctypes.c_size_t(x_u64.shape[0]))
+    assert (back == g['inv_i32']).all()
+    rng = G.rs(9)
+    x = G.torus32(rng, (4, 1024))
+    x[0, :8] = [0, 1, -1, 2**31 - 1, -2**31, -2**31 + 1, 2**30, -2**30]
+    x[1, :] = -2**31
+    x[2, :] = 2**31 - 1
+    out = numpy.empty(x.shape, numpy.uint64)
+    emul.emul_ntt_forward_i32(_p(x), _p(out), ctypes.c_size_t(4))
+    assert (out == O.ntt_forward_i32(x)).all()
+    back = numpy.empty(x.shape, numpy.int32)
+    emul.emul_ntt_inverse_i32(_p(out), _p(back), ctypes.c_size_t(4))
+    assert (back == x).all()
+    y = G.ff_numbers(rng, (3, 1024))
+    back = numpy.empty(y.shape, numpy.int32)
+    emul.emul_ntt_inverse_i32(_p(y), _p(back), ctypes.c_size_t(3))
+    assert (back == O.ntt_inverse_i32(y)).all()
+
+
 def test_lane_field_ops_match_oracle(emul, golden):
     g = golden('arithmetic')
     a, b, s = G.arithmetic_inputs()
