@@ -11,7 +11,7 @@ PTX semantics modelled (32-bit unsigned, one carry flag CC.CF):
     sub.cc / subc[.cc]          d = a - b (- CF);           CF = borrow out
     mad.lo.cc / madc.lo[.cc]    d = lo(a * b) + c (+ CF);   CF = carry out
     mad.hi.cc / madc.hi[.cc]    d = hi(a * b) + c (+ CF);   CF = carry out
-    mul.lo / mul.hi / mul.wide / mad.wide (no flags)
+    mul.lo / mul.hi / mul.wide / mad.wide (no flags); mov.b64 {lo, hi}, x and mov.b64 x, {lo, hi}
 An instruction without `.cc` leaves CF unchanged.  Reading, in a subtract, a flag written by an add (or the
 reverse) raises: ptxas keeps borrows in the inverted sense on the hardware and mixing the two families was
 observed to misbehave, so the source must never do it.
@@ -196,6 +196,10 @@ class Machine:
                 v = get(m.group(3))
                 put(m.group(1), v & M32, 32)
                 put(m.group(2), v >> 32, 32)
+                continue
+            m = re.match(r'mov\.b64\s+(%\d+|\w+)\s*,\s*<(.+)\|(.+)>$', ins)
+            if m:
+                put(m.group(1), get(m.group(2)) | (get(m.group(3)) << 32), 64)
                 continue
             m = re.match(r'([a-z0-9.]+)\s+(.*)$', ins)
             opc, args = m.group(1), [a.strip() for a in m.group(2).split(',')]
