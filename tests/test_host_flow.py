@@ -106,3 +106,30 @@ def test_mask_size_2_flow_against_reference_golden(nufhe, golden):
     assert (ctx.decrypt(sk, r) == g['nand_bits']).all()
     with pytest.raises(ValueError):
         ctx.make_virtual_machine(ck, perf_params=nufhe.PerformanceParameters(ck.params, single_kernel_bootstrap=True))
+
+
+def test_uint_min_views_roll_concatenate(nufhe, k1):
+    """The callers around the path: the `uint_min` circuit on views, `roll`, `concatenate`,
+    `__setitem__` -- host logic only, so it runs on the CPU double."""
+    from nufhe_b200.operators_integer import uint_min, uintarray_to_bitarray, bitarray_to_uintarray
+    ctx, sk, ck = k1
+    vm = ctx.make_virtual_machine(ck)
+    xs = numpy.array([17, 200, 3, 128], numpy.uint8)
+    ys = numpy.array([17, 100, 5, 127], numpy.uint8)
+    ca, cb = ctx.encrypt(sk, uintarray_to_bitarray(xs)), ctx.encrypt(sk, uintarray_to_bitarray(ys))
+    answer = vm.empty_ciphertext((4, 8))
+    uint_min(ctx.thread, ck, answer, ca, cb, perf_params=vm.perf_params)
+    assert (bitarray_to_uintarray(ctx.decrypt(sk, answer)) == numpy.minimum(xs, ys)).all()
+    bits = uintarray_to_bitarray(xs)
+    rolled = ca.copy()
+    rolled.roll(3, axis=-1)
+    assert (ctx.decrypt(sk, rolled) == numpy.roll(bits, 3, axis=-1)).all()
+    both = nufhe.concatenate([ca, cb], axis=0)
+    assert tuple(both.shape) == (8, 8)
+    assert (ctx.decrypt(sk, both) == numpy.concatenate([bits, uintarray_to_bitarray(ys)], axis=0)).all()
+    both[0:4] = cb
+    assert (ctx.decrypt(sk, both[:4]) == uintarray_to_bitarray(ys)).all()
+    view = ca[1:3, ::2]
+    assert tuple(view.shape) == (2, 4)
+    r = vm.gate_not(view)
+    assert (ctx.decrypt(sk, r) == ~bits[1:3, ::2]).all()
