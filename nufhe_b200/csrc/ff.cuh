@@ -19,14 +19,6 @@
 #define NB_D inline
 #endif
 
-// NB_ASM64 = 1 (not measured on the GPU yet, hence off): ff_sub takes and returns 64-bit registers, unpacked / packed
-// with mov.b64 inside the asm block, instead of 32-bit halves glued together in C.  ptxas then keeps more field
-// elements in aligned register pairs: 188 fewer IMAD.MOV per step (8840 -> 8674 instructions, tools/sass_stats.py)
-// and no spill.  The same treatment of the product, the folds and the limb combinations changed nothing.
-#ifndef NB_ASM64
-#define NB_ASM64 0
-#endif
-
 namespace nb {
 
 typedef uint64_t u64;
@@ -78,21 +70,6 @@ template <bool CHAIN> NB_D u64 ff_sub_dev(u64 a, u64 b)
         (void)m;
         return pack(l, h);
     } else {
-#if NB_ASM64
-        u64 d;
-        asm("{\n\t.reg .u32 al, ah, bl, bh, l, h, m, be;\n\t"
-            "mov.b64 {al, ah}, %1;\n\t"
-            "mov.b64 {bl, bh}, %2;\n\t"
-            "sub.cc.u32 l, al, bl;\n\t"
-            "subc.cc.u32 h, ah, bh;\n\t"
-            "subc.u32 m, 0, 0;\n\t"
-            "sub.u32 be, 0, m;\n\t"
-            "add.cc.u32 l, l, be;\n\t"
-            "addc.u32 h, h, m;\n\t"
-            "mov.b64 %0, {l, h};\n\t}"
-            : "=l"(d) : "l"(a), "l"(b));
-        return d;
-#else
         u32 l, h, m, be;
         asm("sub.cc.u32 %0, %4, %6;\n\t"
             "subc.cc.u32 %1, %5, %7;\n\t"
@@ -104,7 +81,6 @@ template <bool CHAIN> NB_D u64 ff_sub_dev(u64 a, u64 b)
             : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
         (void)be;
         return pack(l, h);
-#endif
     }
 }
 #endif

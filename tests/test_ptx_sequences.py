@@ -16,7 +16,7 @@ from ptx_emul import Machine, extract_asm_blocks, preprocess, M32, M64
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RAW = open(os.path.join(ROOT, 'nufhe_b200', 'csrc', 'ff.cuh')).read()
 
-SRC = preprocess(RAW, {'NB_ASM64': 0})
+SRC = preprocess(RAW, {})
 P = (1 << 64) - (1 << 32) + 1
 EPS = (1 << 32) - 1
 
@@ -44,18 +44,9 @@ def run(fn, index=0, **variables):
 
 
 # ---- mirrors of the C glue ------------------------------------------------------------------------
-ASM64 = False          # run ff_sub through its NB_ASM64 form (64-bit asm operands)
-
-
 def ff_sub(a, b, chain=False):
-    # ff_sub_dev<CHAIN>: block 0 = second borrow chain; then the add-chain fold (the one the build uses), with 32-bit
-    # halves (NB_ASM64 = 0) or 64-bit operands (NB_ASM64 = 1)
-    if chain:
-        e = run('ff_sub_dev', 0, a=a, b=b)
-        return HELPERS['pack'](e['l'], e['h'])
-    if ASM64:
-        return run('ff_sub_dev', 1, a=a, b=b)['d']
-    e = run('ff_sub_dev', 1, a=a, b=b)
+    # ff_sub_dev<CHAIN>: block 0 = second borrow chain, block 1 = add-chain fold (the one the build uses)
+    e = run('ff_sub_dev', 0 if chain else 1, a=a, b=b)
     return HELPERS['pack'](e['l'], e['h'])
 
 
@@ -140,19 +131,6 @@ def ff_shl(x, S):
     if s == 96:
         return P - x
     return ff_shl_dev(x, S)
-
-
-@pytest.fixture(params=[0, 1], autouse=True, ids=['halves', 'asm64'])
-def asm64(request):
-    """Every test runs on the default source and on the NB_ASM64 = 1 variant of ff_sub."""
-    global SRC, ASM64
-    ASM64 = bool(request.param)
-    SRC = preprocess(RAW, {'NB_ASM64': request.param})
-    _BLOCKS.clear()
-    yield
-    ASM64 = False
-    SRC = preprocess(RAW, {'NB_ASM64': 0})
-    _BLOCKS.clear()
 
 
 # ---- inputs -------------------------------------------------------------------------------------
