@@ -8,10 +8,10 @@ import numpy
 from .numeric_functions import phase_to_t32
 from .lwe import (
     LweSampleArray, lwe_negate, lwe_copy, lwe_noiseless_trivial, lwe_noiseless_trivial_constant, lwe_add_mul_to,
-    lwe_add_to, lwe_sub_to, lwe_keyswitch, _keyswitch_into)
+    lwe_add_to, lwe_sub_to, lwe_keyswitch)
 from .bootstrap import bootstrap_affine, bootstrap, _single_kernel
 from .tgsw import engine_format
-from .performance import PerformanceParameters, PerformanceParametersForDevice
+from .performance import PerformanceParametersForDevice
 
 
 def get_shape(obj):
@@ -131,7 +131,6 @@ def gate_copy(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, perf_pa
 
 def gate_constant(thr, cloud_key, result: LweSampleArray, vals, perf_params=None):
     """Homomorphic CONSTANT gate: trivial encryptions of the given bits; gates.py:348-387."""
-    import torch
     vals = numpy.asarray(vals)
     if len(vals.shape) > len(result.shape) or vals.shape != tuple(result.shape[len(result.shape) - len(vals.shape):]):
         raise ValueError(

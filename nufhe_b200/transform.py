@@ -5,7 +5,6 @@ The reference renders a Reikna computation per (batch shape, direction, conversi
 kernel per (direction, conversion) handles any batch (`nb_ntt_forward_i32/_u64`, `nb_ntt_inverse_i32/_u64`), so
 `compile(thr)` only binds the engine.  Natural order in and out, results identical to `ntt_transform_ref`."""
 import numpy
-import torch
 
 N = 1024
 

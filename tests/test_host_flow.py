@@ -11,7 +11,6 @@ import numpy
 import pytest
 
 import gen_inputs as G
-from oracle import oracle as O
 from fake_engine import FakeEngine
 
 
