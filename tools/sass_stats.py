@@ -159,7 +159,8 @@ def main():
         w = 0.25 if any(path.endswith('br_phases.cuh') and line in case_lines for path, line in chain) else 1
         counts[phase][pipe] += w
         if args.opcodes and phase.startswith('phase_'):
-            forms[instruction_form(op, m.group(2))] += w * STEP_MULT.get(phase, 1)
+            forms[instruction_form(op, m.group(2))] += w * (
+                1 if ('BrCfgILi1E' in args.kernel and phase.startswith('phase_fwd')) else STEP_MULT.get(phase, 1))
         if args.by_func and chain:
             inner = None
             for path, line in chain:
@@ -171,7 +172,8 @@ def main():
                 inner = fn_of(*chain[0]) or '?'
             byfunc[phase][(inner, pipe)] += w
 
-    mult = STEP_MULT
+    # the wide shape (1 ciphertext on 256 threads) runs the forward phases in one sweep
+    mult = dict(STEP_MULT, phase_fwd1=1, phase_fwd2=1, phase_fwd3=1) if 'BrCfgILi1E' in args.kernel else STEP_MULT
     print('%-22s %7s %7s %7s %7s %7s %8s' % ('phase (static)', 'alu', 'fma', 'lsu', 'uni', 'other', 'total'))
     tot = collections.Counter()
     for phase in sorted(counts):
