@@ -132,3 +132,25 @@ def test_uint_min_views_roll_concatenate(nufhe, k1):
     assert tuple(view.shape) == (2, 4)
     r = vm.gate_not(view)
     assert (ctx.decrypt(sk, r) == ~bits[1:3, ::2]).all()
+
+
+def test_transform_interface_on_the_double():
+    """nufhe's `Transform` / `ForwardTransform` / `InverseTransform` wrappers (nufhe_b200/transform.py): shapes,
+    compile(), round trip, error behaviour -- host logic, the kernels are tested in test_gpu_kernels.py."""
+    import torch
+    from nufhe_b200.transform import Transform, ForwardTransform, InverseTransform, get_transform, transformed_dtype
+    eng = FakeEngine()
+    x = G.torus32(G.rs(1), (2, 3, 1024))
+    fwd = ForwardTransform((2, 3), 1024, None).compile(eng)
+    inv = InverseTransform((2, 3), 1024, None).compile(eng)
+    tr = eng.empty((2, 3, 1024), torch.int64)
+    fwd(tr, eng.to_device(x))
+    back = eng.empty((2, 3, 1024), torch.int32)
+    inv(back, tr)
+    assert (back.numpy() == x).all() and transformed_dtype() == numpy.uint64
+    with pytest.raises(ValueError):
+        Transform(None, (2,))(tr, tr)                   # not compiled
+    with pytest.raises(ValueError):
+        fwd(tr, eng.to_device(x[:1]))                   # wrong batch shape
+    with pytest.raises(ValueError):
+        get_transform('FFT')
