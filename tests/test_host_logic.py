@@ -50,6 +50,10 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, f
                 assert 'libnufhe_oracle' not in src, f
+                assert 'fake_engine' not in src and 'FakeEngine' not in src, f      # the CPU test double stays in tests/
+    for extra in ('bench.py',):
+        src = open(os.path.join(ROOT, extra)).read()
+        assert 'fake_engine' not in src and 'FakeEngine' not in src, extra
 
 
 def test_parameters_and_shapes():
