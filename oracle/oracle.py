@@ -238,6 +238,34 @@ def tgsw_external_mul_k(accum, bk_row):
     return out
 
 
+def bootstrap_k(in_a, in_b, bk, ks=None, mu=MU):
+    """bootstrap() on the multi-kernel path for any mask size k (bootstrap.py:96-229), composed from the restated
+    steps: bk (n, k+1, 2, k+1, N) in the reference's layout, ks for input size k * N.  Returns the key-switched sample
+    (or the extracted one when ks is None) and the final accumulator."""
+    in_a = _c(in_a, numpy.int32)
+    in_b = _c(in_b, numpy.int32)
+    bk = _c(bk, numpy.uint64)
+    B, n, k1 = in_b.size, in_a.shape[-1], bk.shape[1]
+    barb = t32_to_phase(in_b.reshape(B), 2 * N)
+    bara = t32_to_phase(in_a.reshape(B, n), 2 * N)
+    testvect = numpy.full((B, 1, N), mu, numpy.int32)
+    acc = numpy.zeros((B, k1, N), numpy.int32)
+    acc[:, k1 - 1, :] = shift_torus_polynomial(testvect, barb, invert_powers=True)[:, 0, :]
+    for i in range(n):
+        tmp = shift_torus_polynomial(acc, bara, i, minus_one=True)
+        tmp = tgsw_external_mul_k(tmp, bk[i])
+        acc = (acc.view(numpy.uint32) + tmp.view(numpy.uint32)).view(numpy.int32)
+    ext_a = numpy.empty((B, k1 - 1, N), numpy.int32)
+    ext_a[:, :, 0] = acc[:, :k1 - 1, 0]
+    ext_a[:, :, 1:] = (0 - acc[:, :k1 - 1, :0:-1].view(numpy.uint32)).view(numpy.int32)
+    ext_a = ext_a.reshape(B, (k1 - 1) * N)
+    ext_b = numpy.ascontiguousarray(acc[:, k1 - 1, 0])
+    if ks is None:
+        return (ext_a, ext_b), acc
+    ra, rb, _ = lwe_keyswitch(ks[0], ks[1], ks[2], ext_a, ext_b)
+    return (ra, rb), acc
+
+
 def blind_rotate(acc, bk, bara):
     out = _c(acc, numpy.int32).copy()
     bk = _c(bk, numpy.uint64)
@@ -361,51 +389,55 @@ def poly_mul_i32(a, b):
 class OracleKeys:
     """Secret + cloud key material as host arrays, drawn in the reference's order from a seed."""
 
-    def __init__(self, seed, n=LWE_N, make_bk=True):
+    def __init__(self, seed, n=LWE_N, make_bk=True, mask_size=1):
         rng = numpy.random.RandomState(seed)
         self.rng = rng
         self.n = n
+        k = self.mask_size = mask_size
         # (1) LWE key, lwe.py:77-79
         self.lwe_key = rng.randint(0, 2, size=(n,), dtype=numpy.int32)
         # (2) TLWE key, tlwe.py:83-92
-        self.tlwe_key = rng.randint(0, 2, size=(1, N), dtype=numpy.int32)
+        self.tlwe_key = rng.randint(0, 2, size=(k, N), dtype=numpy.int32)
         if not make_bk:
             return
-        # (3) bootstrap key: tlwe_encrypt_zero (tlwe.py:184-197) on shape (n, 2, 2)
-        noises1 = rng.randint(-2**31, 2**31, size=(n, 2, 2, 1, N), dtype=numpy.int32)
-        noises2 = double_to_t32(rng.normal(size=(n, 2, 2, N), scale=BS_STDEV))
+        # (3) bootstrap key: tlwe_encrypt_zero (tlwe.py:184-197) on shape (n, k+1, 2)
+        noises1 = rng.randint(-2**31, 2**31, size=(n, k + 1, 2, k, N), dtype=numpy.int32)
+        noises2 = double_to_t32(rng.normal(size=(n, k + 1, 2, N), scale=BS_STDEV))
         with numpy.errstate(over='ignore'):
-            body = noises2 + poly_mul_i32(self.tlwe_key[0], noises1[:, :, :, 0, :])  # tlwe_cpu.py:76-86
-        bk = numpy.empty((n, 2, 2, 2, N), numpy.int32)
-        bk[:, :, :, 0, :] = noises1[:, :, :, 0, :]
-        bk[:, :, :, 1, :] = body
+            body = noises2.copy()
+            for i in range(k):                                                   # tlwe_cpu.py:76-86
+                body = body + poly_mul_i32(self.tlwe_key[i], numpy.ascontiguousarray(noises1[:, :, :, i, :]))
+        bk = numpy.empty((n, k + 1, 2, k + 1, N), numpy.int32)
+        bk[:, :, :, :k, :] = noises1
+        bk[:, :, :, k, :] = body
         # tgsw_add_message, tgsw_cpu.py:109-126: += s_i * 2^(32-10(j+1)) on the diagonal, coefficient 0
         base_powers = numpy.array([2**22, 2**12], numpy.int32)
         with numpy.errstate(over='ignore'):
-            for mi in range(2):
+            for mi in range(k + 1):
                 bk[:, mi, :, mi, 0] += self.lwe_key[:, None] * base_powers[None, :]
         self.bk_raw = bk
         # tgsw_transform_samples: NTT + Montgomery form (tlwe_gpu.py:199-236)
         out = numpy.empty(bk.shape, numpy.uint64)
         lib().orc_bk_transform(_p(out), _p(bk), _sz(bk.size // N))
         self.bk = out
-        # (4) key-switch key, lwe.py:265-295 + lwe_cpu.py:26-59
+        # (4) key-switch key, lwe.py:265-295 + lwe_cpu.py:26-59; input size k * N
         t, base = KS_T, 2**KS_LOG2_BASE
-        noises_b = rng.normal(size=(N, t, base - 1), scale=KS_STDEV)
+        size_in = k * N
+        noises_b = rng.normal(size=(size_in, t, base - 1), scale=KS_STDEV)
         noises_b -= noises_b.mean()
         noises_b = double_to_t32(noises_b)
-        noises_a = rng.randint(-2**31, 2**31, size=(N, t, base - 1, n), dtype=numpy.int32)
+        noises_a = rng.randint(-2**31, 2**31, size=(size_in, t, base - 1, n), dtype=numpy.int32)
         in_key = self.tlwe_key.ravel()
         hs = numpy.arange(1, base).astype(numpy.int32)
         js = numpy.arange(t).astype(numpy.int32)
         with numpy.errstate(over='ignore'):
             messages = (in_key[:, None, None] * hs[None, None, :]
                         * (2**(32 - (js[None, :, None] + 1) * KS_LOG2_BASE)).astype(numpy.int32))
-        dot = numpy.empty((N, t, base - 1), numpy.int32)
-        lib().orc_lwe_dot(_p(dot), _p(noises_a), _p(self.lwe_key), _sz(N * t * (base - 1)), _sz(n))
-        self.ks_a = numpy.zeros((N, t, base, n), numpy.int32)
-        self.ks_b = numpy.zeros((N, t, base), numpy.int32)
-        self.ks_cv = numpy.zeros((N, t, base), numpy.float32)
+        dot = numpy.empty((size_in, t, base - 1), numpy.int32)
+        lib().orc_lwe_dot(_p(dot), _p(noises_a), _p(self.lwe_key), _sz(size_in * t * (base - 1)), _sz(n))
+        self.ks_a = numpy.zeros((size_in, t, base, n), numpy.int32)
+        self.ks_b = numpy.zeros((size_in, t, base), numpy.int32)
+        self.ks_cv = numpy.zeros((size_in, t, base), numpy.float32)
         self.ks_a[:, :, 1:, :] = noises_a
         with numpy.errstate(over='ignore'):
             self.ks_b[:, :, 1:] = (messages.astype(numpy.int32) + noises_b + dot)

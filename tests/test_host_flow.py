@@ -154,3 +154,27 @@ def test_transform_interface_on_the_double():
         fwd(tr, eng.to_device(x[:1]))                   # wrong batch shape
     with pytest.raises(ValueError):
         get_transform('FFT')
+
+
+def test_mask_size_2_gates_against_the_general_oracle(nufhe):
+    """Beyond the golden: a small batch of k = 2 gates through the host layer equals the oracle's general-k bootstrap
+    (oracle.bootstrap_k, itself pinned to the reference's k = 2 closures in test_oracle.py)."""
+    from oracle import oracle as O
+    seed = 424242
+    ctx = nufhe.Context(rng=nufhe.DeterministicRNG(seed), thread=FakeEngine())
+    sk, ck = ctx.make_key_pair(tlwe_mask_size=2)
+    keys = O.OracleKeys(seed, mask_size=2)
+    assert (host(ck.bootstrap_key.tgsw.samples.a.coeffs, True) == keys.bk).all()
+    assert (host(ck.keyswitch_key.lwe.a) == keys.ks_a).all() and (host(ck.keyswitch_key.lwe.b) == keys.ks_b).all()
+    a = numpy.array([True, False, True])
+    b = numpy.array([False, False, True])
+    ca, cb = ctx.encrypt(sk, a), ctx.encrypt(sk, b)
+    oa, ob = keys.encrypt(a), keys.encrypt(b)
+    assert (host(ca.a) == oa[0]).all() and (host(cb.b) == ob[1]).all()
+    vm = ctx.make_virtual_machine(ck)
+    for name, (num, den, sa, sb) in (('gate_or', O.GATE_TABLE['or']), ('gate_andyn', O.GATE_TABLE['andyn'])):
+        r = getattr(vm, name)(ca, cb)
+        t_a, t_b = O.lwe_affine2(oa, ob, O.phase_to_t32(num, den), sa, sb)
+        (wa, wb), _ = O.bootstrap_k(t_a, t_b, keys.bk, keys.ks)
+        assert (host(r.a) == wa).all() and (host(r.b) == wb).all(), name
+    assert (ctx.decrypt(sk, vm.gate_or(ca, cb)) == (a | b)).all()

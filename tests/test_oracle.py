@@ -151,3 +151,33 @@ def test_mask_size_2_steps(golden):
     assert (O.tgsw_decompose_k(accum_full) == g1['decomp']).all()
     assert (O.tgsw_mac_k(tr_sample, bk1[1]) == g1['mac']).all()
     assert (O.tgsw_external_mul_k(accum_full, bk1[0]) == g1['ext_full']).all()
+
+
+def test_mask_size_2_keys_and_gate(golden):
+    """Oracle key generation and the whole bootstrap for tlwe_mask_size = 2 against the reference's closures
+    (tests/golden/k2.npz): key digests, ciphertexts, the final accumulator, the extracted and the key-switched sample."""
+    import hashlib
+    g = golden('k2')
+    keys = O.OracleKeys(int(g['seed']), mask_size=2)
+
+    def sha(a):
+        return hashlib.sha256(numpy.ascontiguousarray(a).tobytes()).hexdigest()
+    assert sha(keys.lwe_key) == str(g['lwe_key_sha']) and sha(keys.tlwe_key) == str(g['tlwe_key_sha'])
+    assert sha(keys.bk_raw) == str(g['bk_raw_sha']) and sha(keys.bk) == str(g['bk_sha'])
+    assert sha(keys.ks_a) == str(g['ks_a_sha']) and sha(keys.ks_b) == str(g['ks_b_sha'])
+    c1, c2 = keys.encrypt(G.GATE_BITS_A[:2]), keys.encrypt(G.GATE_BITS_B[:2])
+    assert (c1[0] == g['c1_a']).all() and (c1[1] == g['c1_b']).all() and (c2[0] == g['c2_a']).all()
+    t_a, t_b = O.lwe_affine2(c1, c2, O.phase_to_t32(1, 8), -1, -1)
+    (ra, rb), acc = O.bootstrap_k(t_a, t_b, keys.bk, keys.ks)
+    assert (acc == g['nand_acc']).all()
+    assert (ra == g['nand_a']).all() and (rb == g['nand_b']).all()
+    (ea, eb), _ = O.bootstrap_k(t_a, t_b, keys.bk, None)
+    assert (ea == g['nand_ext_a']).all() and (eb == g['nand_ext_b']).all()
+    assert (keys.decrypt((ra, rb)) == g['nand_bits']).all()
+    # and the same composition at k = 1 equals the fused restatement
+    k1 = O.OracleKeys(G.GATE_SEED)
+    a, b = k1.encrypt([True, False]), k1.encrypt([True, True])
+    t_a, t_b = O.lwe_affine2(a, b, O.phase_to_t32(1, 8), -1, -1)
+    (ra, rb), _ = O.bootstrap_k(t_a, t_b, k1.bk, k1.ks)
+    want = O.bootstrap(t_a, t_b, k1.bk, k1.ks)
+    assert (ra == want[0]).all() and (rb == want[1]).all()
