@@ -115,7 +115,8 @@ int nb_lwe_affine(nb_ctx *ctx, int32_t *res_a, int32_t *res_b, const int32_t *x1
 int nb_shift_torus_polynomial(nb_ctx *ctx, int32_t *result, const int32_t *source, const int32_t *powers,
                               size_t powers_stride, size_t power_idx, int polys_per_power, int mode, int n_log2,
                               size_t polys);
-/* tlwe_noiseless_trivial (tlwe.py:156-158): acc (B, k+1, N) = (0, .., 0, mu (B, N)); cv (B, k+1) = 0 (may be NULL) */
+/* tlwe_noiseless_trivial (tlwe.py:156-158): acc (B, k+1, N) = (0, .., 0, mu (B, N)); cv (B,) = 0, one variance per
+ * sample (may be NULL) */
 int nb_tlwe_noiseless_trivial(nb_ctx *ctx, int32_t *acc, float *cv, const int32_t *mu, int mask_size, int n_log2,
                               size_t batch);
 /* tlwe_extract_lwe_samples (tlwe.py:161-165): out_a (B, k*N), out_b (B,) from acc (B, k+1, N) */

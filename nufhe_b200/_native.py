@@ -19,7 +19,7 @@ _sz = ctypes.c_size_t
 _i32 = ctypes.c_int32
 _int = ctypes.c_int
 
-# name -> argtypes; mirrors include/nufhe_b200.h exactly (tests/test_capi_symbols.py checks the header)
+# name -> argtypes; mirrors include/nufhe_b200.h exactly (tests/test_host_logic.py checks it against the header)
 SIGNATURES = {
     'nb_ctx_create': [_int, _vp, ctypes.POINTER(_vp)],
     'nb_ctx_destroy': [_vp],

@@ -40,6 +40,26 @@ static int check(nb_ctx *ctx, cudaError_t e, const char *what)
 
 static int launch_check(nb_ctx *ctx, const char *what) { return check(ctx, cudaGetLastError(), what); }
 
+// Every entry point works on ctx->device and leaves the caller's current device as it found it (one process may
+// hold several engines, one per GPU, like the reference's one-Context-per-device model, api_high_level.py:153-181).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define NB_ON_DEVICE(ctx)                   \
+    DeviceGuard _guard((ctx)->device);      \
+    NB_TRY(check(ctx, _guard.err, "cudaSetDevice"))
+
 extern "C" {
 
 int nb_ctx_create(int device, void *stream, nb_ctx **out)
@@ -51,7 +71,7 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     ctx->stream = (cudaStream_t)stream;
     ctx->d_ph_fwd = ctx->d_ph_inv = ctx->d_ones512 = nullptr;
     *out = ctx;   // returned even on failure so that nb_last_error() can be read; caller destroys it
-    NB_TRY(check(ctx, cudaSetDevice(device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     cudaDeviceProp prop;
     NB_TRY(check(ctx, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"));
     ctx->sm_count = prop.multiProcessorCount;
@@ -87,7 +107,7 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
 void nb_ctx_destroy(nb_ctx *ctx)
 {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     if (ctx->d_ph_fwd) cudaFree(ctx->d_ph_fwd);
     if (ctx->d_ph_inv) cudaFree(ctx->d_ph_inv);
     if (ctx->d_ones512) cudaFree(ctx->d_ones512);
@@ -106,7 +126,7 @@ int nb_ctx_set_stream(nb_ctx *ctx, void *stream)
 int nb_ctx_synchronize(nb_ctx *ctx)
 {
     if (!ctx) return NB_EINVAL;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     return check(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
 }
 
@@ -140,7 +160,7 @@ int nb_ntt_forward_i32(nb_ctx *ctx, const int32_t *in, uint64_t *out, size_t bat
     if (!ctx) return NB_EINVAL;
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_i32: null argument");
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     ntt_forward_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<i32>");
 }
@@ -150,7 +170,7 @@ int nb_ntt_forward_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
     if (!ctx) return NB_EINVAL;
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_u64: null argument");
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     ntt_forward_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<u64>");
 }
@@ -160,7 +180,7 @@ int nb_ntt_inverse_i32(nb_ctx *ctx, const uint64_t *in, int32_t *out, size_t bat
     if (!ctx) return NB_EINVAL;
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_i32: null argument");
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     ntt_inverse_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<i32>");
 }
@@ -170,7 +190,7 @@ int nb_ntt_inverse_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
     if (!ctx) return NB_EINVAL;
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_u64: null argument");
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     ntt_inverse_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<u64>");
 }
@@ -182,7 +202,7 @@ int nb_ff_elementwise(nb_ctx *ctx, int op, const uint64_t *a, const uint64_t *b,
     if (op < 0 || op > NB_FF_LSH_CONST) return fail(ctx, NB_EINVAL, "nb_ff_elementwise: unknown op");
     if (op != NB_FF_PREPARE && !b) return fail(ctx, NB_EINVAL, "nb_ff_elementwise: binary op needs b");
     if (n == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     size_t blocks = (n + 255) / 256, cap = (size_t)ctx->sm_count * 16;
     ff_elementwise_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
         op, (const u64 *)a, (const u64 *)b, (u64 *)out, n, b_period);
@@ -195,7 +215,7 @@ int nb_bk_prepare(nb_ctx *ctx, const uint64_t *bk_ref, uint64_t *bk_int, size_t 
 {
     if (!ctx || !bk_ref || !bk_int) return fail(ctx, NB_EINVAL, "nb_bk_prepare: null argument");
     if (rows == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     size_t total = rows * NTT_N, blocks = (total + 255) / 256, cap = (size_t)ctx->sm_count * 16;
     bk_prepare_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>((const u64 *)bk_ref, (u64 *)bk_int,
                                                                                   ctx->d_ones512, rows);
@@ -220,7 +240,7 @@ int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, siz
 {
     if (!ctx || !accum || !bk_int) return fail(ctx, NB_EINVAL, "nb_external_product: null argument");
     if (batch == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     BlindRotateArgs p{};
     p.accum = accum; p.accum_out = accum; p.bk = (const u64 *)bk_int + bk_row * BK_ROW_U64;
     p.plain = 1; p.batch = batch; p.sm_count = ctx->sm_count; p.stagger_cycles = 0;
@@ -232,7 +252,7 @@ static int launch_blind_rotate(nb_ctx *ctx, BlindRotateArgs &p)
 {
     if (p.n <= 0 || p.n > LWE_N_MAX) return fail(ctx, NB_EUNSUPPORTED, "LWE dimension out of range");
     if (p.batch == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     p.sm_count = ctx->sm_count;
     p.stagger_cycles = ctx->stagger_cycles;
     launch_br(ctx, p);
@@ -293,7 +313,7 @@ int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, cons
     if (n + 1 > 512) return fail(ctx, NB_EUNSUPPORTED, "nb_keyswitch: output LWE dimension above 511");
     if (t < 1 || log2_base < 1 || t * log2_base > 31) return fail(ctx, NB_EINVAL, "nb_keyswitch: bad decomposition");
     if (batch == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     KeyswitchArgs p{};
     p.src1_a = src1_a; p.src1_b = src1_b; p.src2_a = src2_a; p.src2_b = src2_b; p.c = c;
     p.ks_a = ks_a; p.ks_b = ks_b; p.ks_cv = ks_cv; p.res_a = res_a; p.res_b = res_b; p.res_cv = res_cv;
@@ -314,7 +334,6 @@ int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, cons
         if (splits > 1) {
             NB_TRY(check(ctx, cudaMemsetAsync(res_a, 0, batch * n * sizeof(int32_t), ctx->stream), "cudaMemsetAsync"));
             NB_TRY(check(ctx, cudaMemsetAsync(res_b, 0, batch * sizeof(int32_t), ctx->stream), "cudaMemsetAsync"));
-            if (res_cv) NB_TRY(check(ctx, cudaMemsetAsync(res_cv, 0, batch * sizeof(float), ctx->stream), "cudaMemsetAsync"));
         }
         keyswitch_kernel<<<dim3(grid, splits), KS_THREADS, KS_SMEM_BYTES, ctx->stream>>>(p);
     } else {
@@ -339,7 +358,7 @@ int nb_shift_torus_polynomial(nb_ctx *ctx, int32_t *result, const int32_t *sourc
     if (n_log2 < 1 || n_log2 > 20 || polys_per_power < 1) return fail(ctx, NB_EINVAL, "nb_shift_torus_polynomial: bad size");
     if (result == source) return fail(ctx, NB_EINVAL, "nb_shift_torus_polynomial: result must not alias source");
     if (polys == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     shift_torus_polynomial_kernel<<<ew_grid(ctx, polys << n_log2), 256, 0, ctx->stream>>>(
         result, source, powers, powers_stride, power_idx, polys_per_power, mode, n_log2, polys);
     return launch_check(ctx, "shift_torus_polynomial_kernel");
@@ -352,7 +371,7 @@ int nb_tlwe_noiseless_trivial(nb_ctx *ctx, int32_t *acc, float *cv, const int32_
     if (!acc || !mu) return fail(ctx, NB_EINVAL, "nb_tlwe_noiseless_trivial: null argument");
     if (mask_size < 1 || n_log2 < 1 || n_log2 > 20) return fail(ctx, NB_EINVAL, "nb_tlwe_noiseless_trivial: bad size");
     if (batch == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     tlwe_noiseless_trivial_kernel<<<ew_grid(ctx, (batch * (mask_size + 1)) << n_log2), 256, 0, ctx->stream>>>(
         acc, cv, mu, mask_size, n_log2, batch);
     return launch_check(ctx, "tlwe_noiseless_trivial_kernel");
@@ -365,7 +384,7 @@ int nb_tlwe_extract_lwe_samples(nb_ctx *ctx, int32_t *out_a, int32_t *out_b, con
     if (!out_a || !out_b || !acc) return fail(ctx, NB_EINVAL, "nb_tlwe_extract_lwe_samples: null argument");
     if (mask_size < 1 || n_log2 < 1 || n_log2 > 20) return fail(ctx, NB_EINVAL, "nb_tlwe_extract_lwe_samples: bad size");
     if (batch == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     tlwe_extract_lwe_samples_kernel<<<ew_grid(ctx, (batch * mask_size) << n_log2), 256, 0, ctx->stream>>>(
         out_a, out_b, acc, mask_size, n_log2, batch);
     return launch_check(ctx, "tlwe_extract_lwe_samples_kernel");
@@ -377,7 +396,7 @@ int nb_t32_to_phase(nb_ctx *ctx, int32_t *out, const int32_t *in, size_t n, uint
     if (!out || !in) return fail(ctx, NB_EINVAL, "nb_t32_to_phase: null argument");
     if (mspace_size == 0 || (mspace_size & (mspace_size - 1))) return fail(ctx, NB_EINVAL, "nb_t32_to_phase: mspace_size must be a power of two");
     if (n == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     t32_to_phase_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(out, in, n, mspace_size);
     return launch_check(ctx, "t32_to_phase_kernel");
 }
@@ -390,7 +409,7 @@ int nb_tgsw_decompose(nb_ctx *ctx, int32_t *out, const int32_t *in, size_t polys
     if (decomp_length < 1 || bs_log2_base < 1 || decomp_length * bs_log2_base > 32 || n_log2 < 1 || n_log2 > 20)
         return fail(ctx, NB_EINVAL, "nb_tgsw_decompose: bad decomposition");
     if (polys == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     tgsw_decompose_kernel<<<ew_grid(ctx, (polys * decomp_length) << n_log2), 256, 0, ctx->stream>>>(
         out, in, polys, decomp_length, bs_log2_base, offset, n_log2);
     return launch_check(ctx, "tgsw_decompose_kernel");
@@ -403,7 +422,7 @@ int nb_tgsw_mac(nb_ctx *ctx, uint64_t *out, const uint64_t *tr, const uint64_t *
     if (!out || !tr || !bk_row) return fail(ctx, NB_EINVAL, "nb_tgsw_mac: null argument");
     if (mask_size < 1 || mask_size > 15 || decomp_length < 1 || decomp_length > 32) return fail(ctx, NB_EINVAL, "nb_tgsw_mac: bad size");
     if (batch == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     tgsw_mac_kernel<<<ew_grid(ctx, batch * (mask_size + 1) * NTT_N), 256, 0, ctx->stream>>>(
         (u64 *)out, (const u64 *)tr, (const u64 *)bk_row, batch, mask_size + 1, decomp_length);
     return launch_check(ctx, "tgsw_mac_kernel");
@@ -417,7 +436,7 @@ int nb_tlwe_add_to(nb_ctx *ctx, int32_t *res, const int32_t *src, size_t n, floa
         return fail(ctx, NB_EINVAL, "nb_tlwe_add_to: null argument");
     if (n_cv > n) return fail(ctx, NB_EINVAL, "nb_tlwe_add_to: more variances than coefficients");
     if (n == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     add_to_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(res, src, n, res_cv, src_cv, res_cv ? n_cv : 0);
     return launch_check(ctx, "add_to_kernel");
 }
@@ -430,7 +449,7 @@ int nb_lwe_affine(nb_ctx *ctx, int32_t *res_a, int32_t *res_b, const int32_t *x1
     if ((x1_a == nullptr) != (x1_b == nullptr) || (x2_a == nullptr) != (x2_b == nullptr))
         return fail(ctx, NB_EINVAL, "nb_lwe_affine: a/b parts must come together");
     if (batch == 0) return NB_OK;
-    NB_TRY(check(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+    NB_ON_DEVICE(ctx);
     size_t total = batch * (n + 1), blocks = (total + 255) / 256, cap = (size_t)ctx->sm_count * 16;
     lwe_affine_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
         res_a, res_b, x1_a, x1_b, x2_a, x2_b, c, s1, s2, batch, (int)n);

@@ -231,11 +231,12 @@ NB_D int br2_rotation(const BlindRotateArgs &p, size_t c, int i)
     if (p.bara) return p.bara[c * p.n + i];
     if (p.job_batch && c >= p.job_batch) {
         const size_t d = c - p.job_batch;
-        i32 xa = p.j2_s1 * p.j2_in1_a[d * p.n + i] + (p.j2_in2_a ? p.j2_s2 * p.j2_in2_a[d * p.n + i] : 0);
-        return modswitch_2n(xa);
+        u32 xa = (u32)p.j2_s1 * (u32)p.j2_in1_a[d * p.n + i] + (p.j2_in2_a ? (u32)p.j2_s2 * (u32)p.j2_in2_a[d * p.n + i] : 0u);
+        return modswitch_2n((i32)xa);
     }
-    i32 xa = p.s1 * p.in1_a[c * p.n + i] + (p.in2_a ? p.s2 * p.in2_a[c * p.n + i] : 0);
-    return modswitch_2n(xa);
+    // Torus32 arithmetic wraps by design (XOR / XNOR use s = +-2): unsigned, like lwe_affine_kernel
+    u32 xa = (u32)p.s1 * (u32)p.in1_a[c * p.n + i] + (p.in2_a ? (u32)p.s2 * (u32)p.in2_a[c * p.n + i] : 0u);
+    return modswitch_2n((i32)xa);
 }
 
 template <bool ROTATE, class Cfg>
@@ -295,14 +296,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_k
             val = p.accum[(c * 2 + mi) * NTT_N + x];
         } else {
             // ACC = (0, X^(2N - barb) * [mu, ..., mu])   (bootstrap.py:177-182, 224)
-            i32 xb;
+            u32 xb;
             if (p.job_batch && c >= p.job_batch) {
                 const size_t d = c - p.job_batch;
-                xb = p.j2_c + p.j2_s1 * p.j2_in1_b[d] + (p.j2_in2_b ? p.j2_s2 * p.j2_in2_b[d] : 0);
+                xb = (u32)p.j2_c + (u32)p.j2_s1 * (u32)p.j2_in1_b[d] + (p.j2_in2_b ? (u32)p.j2_s2 * (u32)p.j2_in2_b[d] : 0u);
             } else {
-                xb = p.c + p.s1 * p.in1_b[c] + (p.in2_b ? p.s2 * p.in2_b[c] : 0);
+                xb = (u32)p.c + (u32)p.s1 * (u32)p.in1_b[c] + (p.in2_b ? (u32)p.s2 * (u32)p.in2_b[c] : 0u);
             }
-            int q = 2 * NTT_N - modswitch_2n(xb);
+            int q = 2 * NTT_N - modswitch_2n((i32)xb);
             if (q < NTT_N) val = x < q ? (i32)(0u - (u32)p.mu) : p.mu;
             else val = x < q - NTT_N ? p.mu : (i32)(0u - (u32)p.mu);
             if (mi == 0) val = 0;
@@ -379,7 +380,7 @@ __global__ void tlwe_noiseless_trivial_kernel(i32 *__restrict__ acc, float *__re
         const size_t c = i / per, r = i % per;
         const int poly = (int)(r >> n_log2), x = (int)(r & (N - 1));
         acc[i] = poly == mask_size ? mu[c * N + x] : 0;
-        if (cv && i < batch * (size_t)(mask_size + 1)) cv[i] = 0.f;
+        if (cv && i < batch) cv[i] = 0.f;            // one variance per sample: cv is (B,) (tlwe.py:94-112)
     }
 }
 
@@ -573,6 +574,24 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
             cv += d == 0 ? kc.x : d == 1 ? kc.y : d == 2 ? kc.z : kc.w;
             kb = kb_next; kc = kc_next;
         }
+        if (split && blockIdx.y == 0 && p.res_cv) {
+            // The variance is a float32 running sum in (j, k) order (lwe_cpu.py:90-93); float addition is not
+            // associative, so with split j-ranges the y = 0 CTA alone walks all 1024 coefficients (from global
+            // memory: its shared-memory digits cover its own slice only).  Same order as the unsplit path.
+            cv = 0.f;
+            const size_t row = (ct0 + min(q, nct - 1)) * KS_IN;
+            for (int j = 0; j < KS_IN; j++) {
+                u32 v = (u32)__ldg(p.src1_a + row + j);
+                if (p.src2_a) v += (u32)__ldg(p.src2_a + row + j);
+                const u32 bits = (v + prec_offset) >> 16;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float4 kc4 = __ldg(reinterpret_cast<const float4 *>(p.ks_cv) + j * 8 + k);
+                    const u32 d = (bits >> (14 - 2 * k)) & 3u;
+                    cv += d == 0 ? kc4.x : d == 1 ? kc4.y : d == 2 ? kc4.z : kc4.w;
+                }
+            }
+        }
         if (q < nct) {
             u32 b = (u32)p.src1_b[ct0 + q] + (p.src2_b ? (u32)p.src2_b[ct0 + q] : 0u) + (u32)p.c;
             if (!split) {
@@ -580,7 +599,7 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
                 if (p.res_cv) p.res_cv[ct0 + q] = cv;
             } else {
                 atomicAdd(reinterpret_cast<unsigned int *>(p.res_b + ct0 + q), (blockIdx.y == 0 ? b : 0u) + accb);
-                if (p.res_cv) atomicAdd(p.res_cv + ct0 + q, cv);
+                if (p.res_cv && blockIdx.y == 0) p.res_cv[ct0 + q] = cv;
             }
         }
         return;

@@ -15,41 +15,45 @@ from .performance import PerformanceParametersForDevice
 
 
 def get_shape(obj):
-    if hasattr(obj, 'shape'):
-        return tuple(obj.shape)
-    elif isinstance(obj, list):
-        return numpy.asarray(obj).shape
-    else:
-        raise ValueError("An object of type " + str(type(obj)) + " is not array-like")
-
-
-def _result_shape_pair(shape1, shape2):
-    if len(shape1) > len(shape2):
-        shape2 = (1,) * (len(shape1) - len(shape2)) + shape2
-    else:
-        shape1 = (1,) * (len(shape2) - len(shape1)) + shape1
-    if any((l1 != l2 and l1 > 1 and l2 > 1) for l1, l2 in zip(shape1, shape2)):
-        raise ValueError("Incompatible shapes: {s1}, {s2}".format(s1=shape1, s2=shape2))
-    return tuple((l1 if l1 > 1 else l2) for l1, l2 in zip(shape1, shape2))
+    """Message shape of a gate argument: anything with `.shape`, or a (nested) list of bits
+    (behaviour of gates.py:40-46)."""
+    shape = getattr(obj, 'shape', None)
+    if shape is not None:
+        return tuple(shape)
+    if isinstance(obj, list):
+        return numpy.shape(obj)
+    raise ValueError("An object of type %s is not array-like" % type(obj))
 
 
 def result_shape(*shapes):
-    shapes = [tuple(s) for s in shapes]
+    """Shape of a gate result for arguments of the given message shapes: right-aligned, an extent of 1 (or a missing
+    leading axis) stretches to the other arguments' extent, two different extents above 1 do not combine
+    (what gates.py:49-68 computes pair by pair)."""
     if len(shapes) == 1:
-        return shapes[0]
-    elif len(shapes) == 2:
-        return _result_shape_pair(*shapes)
-    else:
-        return _result_shape_pair(shapes[0], result_shape(*shapes[1:]))
+        return tuple(shapes[0])
+    rank = max(len(shape) for shape in shapes)
+    extents = [1] * rank
+    for shape in shapes:
+        for axis, extent in enumerate(shape, rank - len(shape)):
+            have = extents[axis]
+            if extent > 1 and have > 1 and extent != have:
+                raise ValueError("Incompatible shapes: " + ", ".join(str(tuple(s)) for s in shapes))
+            if have <= 1:
+                extents[axis] = extent
+    return tuple(extents)
+
+
+def _check_broadcast(derived, dest_shape, what):
+    dest_shape = tuple(dest_shape)
+    if len(derived) > len(dest_shape) or derived != dest_shape[len(dest_shape) - len(derived):]:
+        raise ValueError("The shape of %s %s cannot be broadcasted to the shape of the destination %s"
+                         % (what, derived, dest_shape))
 
 
 def check_shape(result, *args):
-    rshape = result_shape(*[arg.shape for arg in args])
-    if len(rshape) > len(result.shape) or rshape != tuple(result.shape[len(result.shape) - len(rshape):]):
-        raise ValueError(
-            ("The shape of the result derived from the arguments {derived_shape} "
-             "cannot be broadcasted to the shape of the destination {dest_shape}").format(
-                derived_shape=rshape, dest_shape=tuple(result.shape)))
+    """The broadcast shape of the arguments has to be the trailing part of the destination's shape (gates.py:71-78)."""
+    _check_broadcast(result_shape(*[tuple(arg.shape) for arg in args]), result.shape,
+                     "the result derived from the arguments")
 
 
 MU = phase_to_t32(1, 8)
@@ -132,10 +136,8 @@ def gate_copy(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, perf_pa
 def gate_constant(thr, cloud_key, result: LweSampleArray, vals, perf_params=None):
     """Homomorphic CONSTANT gate: trivial encryptions of the given bits; gates.py:348-387."""
     vals = numpy.asarray(vals)
-    if len(vals.shape) > len(result.shape) or vals.shape != tuple(result.shape[len(result.shape) - len(vals.shape):]):
-        raise ValueError(
-            ("The shape of the values {vshape} cannot be broadcasted to the shape "
-             "of the destination {dest_shape}").format(vshape=vals.shape, dest_shape=tuple(result.shape)))
+    # the same rule as for ciphertext arguments (gates.py:371: check_shape(result, vals)): size-1 axes broadcast
+    _check_broadcast(result_shape(tuple(vals.shape)), result.shape, "the values")
     mus = numpy.where(vals.astype(bool), MU, -MU).astype(numpy.int32)
     lwe_noiseless_trivial(thr, result, thr.to_device(numpy.ascontiguousarray(mus)))
 

@@ -98,6 +98,11 @@ def test_parameters_and_shapes():
         check_shape(S((2, 3)), S((5, 2, 3)))
     with pytest.raises(ValueError):
         check_shape(S((2, 4)), S((2, 3)))
+    with pytest.raises(ValueError):                   # the derived shape must EQUAL the trailing dims (gates.py:73)
+        check_shape(S((3, 4)), S((1, 4)))
+    check_shape(S((3, 4)), S((4,)))
+    check_shape(S((3, 4)), S(()))                     # a scalar (gate_constant with one bit)
+    assert result_shape((1, 4)) == (1, 4) and result_shape((7,), (1,)) == (7,)
 
 
 def test_encodings():
@@ -121,6 +126,31 @@ def test_rng_matches_reference_semantics():
     assert s.uniform_torus32((9,)).dtype == numpy.int32
     g = s.gauss((1001,), 2.0)
     assert g.shape == (1001,) and 1.0 < g.std() < 3.0
+
+
+def test_secure_rng_statistics():
+    """SecureRNG is our own sampler (no seed, nothing to match byte for byte): check the distributions instead.
+    Bounds are ~6 sigma of the estimator, so a correct sampler fails with probability < 1e-8."""
+    from scipy import stats
+    import nufhe_b200 as nufhe
+    s = nufhe.SecureRNG()
+    n = 400000
+    bits = s.uniform_bool((n,))
+    assert bits.dtype == numpy.int32 and abs(bits.mean() - 0.5) < 6 * 0.5 / n**0.5
+    t = s.uniform_torus32((n,)).astype(numpy.float64) / 2**32
+    assert abs(t.mean()) < 6 * (1 / 12**0.5) / n**0.5 and abs(t.var() - 1 / 12) < 0.002
+    assert stats.kstest(t + 0.5, 'uniform').pvalue > 1e-6
+    u = s._open_unit_interval(n)
+    assert u.min() > 0.0 and u.max() < 1.0                     # open interval: log(u) is always finite
+    sigma = 1 / 2**15 * (2 / numpy.pi)**0.5                    # the scheme's LWE noise, api_low_level.py:58-59
+    g = s.gauss((n + 1,), sigma)                               # odd count: the last pair is cut
+    assert g.shape == (n + 1,) and numpy.isfinite(g).all()
+    assert abs(g.mean()) < 6 * sigma / n**0.5 and abs(g.std() / sigma - 1) < 6 / (2 * n)**0.5
+    assert stats.kstest(g / sigma, 'norm').pvalue > 1e-6
+    assert abs(stats.kurtosis(g)) < 0.05 and abs(stats.skew(g)) < 0.03
+    assert s.gauss((2, 3, 5), 1.0).shape == (2, 3, 5)
+    # the two halves of the polar pairs are uncorrelated
+    assert abs(numpy.corrcoef(g[:n // 2], g[n // 2:n])[0, 1]) < 6 / (n // 2)**0.5
 
 
 # ---- the per-lane GPU transform code, executed on the host (csrc/host_emul.cpp) ------------------
