@@ -139,6 +139,19 @@ int nb_tgsw_mac(nb_ctx *ctx, uint64_t *out, const uint64_t *tr, const uint64_t *
 int nb_tlwe_add_to(nb_ctx *ctx, int32_t *res, const int32_t *src, size_t n, float *res_cv, const float *src_cv,
                    size_t n_cv);
 
+/* LweEncrypt / LweDecrypt (lwe_gpu.py:186-284, kernels lwe_gpu.mako:205-262; lwe.py:325-343): the wrap-around dot
+ * product of LWE masks a (B, n) with the binary key (n),
+ *     out[i] = add1[i] (+ add2[i]) + sign * <a[i, :], key>       (add1, add2 may be NULL)
+ * encrypt: out = b, add1 = messages, add2 = noises_b, sign = +1;  decrypt phase: add1 = b, sign = -1. */
+int nb_lwe_dot(nb_ctx *ctx, int32_t *out, const int32_t *a, const int32_t *key, const int32_t *add1,
+               const int32_t *add2, int32_t sign, size_t batch, size_t n);
+/* MakeLweKeyswitchKey (lwe_gpu.py:63-124, kernel lwe_gpu.mako:18-56; lwe.py:265-295): ks_a (in, t, base, n),
+ * ks_b / ks_cv (in, t, base) from in_key (in), out_key (n), noises_a (in, t, base-1, n), noises_b (in, t, base-1):
+ * row h = 0 is zero, row h encrypts in_key[i] * h * 2^(32 - (j+1) log2_base) with variance noise_variance. */
+int nb_make_keyswitch_key(nb_ctx *ctx, int32_t *ks_a, int32_t *ks_b, float *ks_cv, const int32_t *in_key,
+                          const int32_t *out_key, const int32_t *noises_a, const int32_t *noises_b, size_t in_size,
+                          size_t n, int t, int log2_base, float noise_variance);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,8 @@ SIGNATURES = {
     'nb_t32_to_phase': [_vp, _vp, _vp, _sz, ctypes.c_uint32],
     'nb_tgsw_decompose': [_vp, _vp, _vp, _sz, _int, _int, _i32, _int],
     'nb_tgsw_mac': [_vp, _vp, _vp, _vp, _sz, _int, _int],
+    'nb_lwe_dot': [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _sz, _sz],
+    'nb_make_keyswitch_key': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _int, _int, ctypes.c_float],
 }
 _RESTYPES = {'nb_bk_row_u64': ctypes.c_size_t, 'nb_ctx_destroy': None, 'nb_last_error': ctypes.c_char_p, 'nb_build_info': ctypes.c_char_p}
 

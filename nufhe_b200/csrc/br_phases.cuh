@@ -31,6 +31,28 @@ namespace nb {
 #ifndef NB_BR_CT
 #define NB_BR_CT 2
 #endif
+// Deferred canonicalisation: the general multiplications of fwd1 / inv1 and the MAC leave their result as "some
+// 64-bit value of the right residue" (ff_mul_nc, ff_dot4_sub_nc) instead of paying 6 ALU instructions per element
+// for the conditional subtraction of p.  Such a value is above p with probability 2^-32 (a few elements per
+// 4096-ciphertext bootstrap), and then its high limb is 2^32 - 1: every thread keeps the maximum of the high limbs
+// it produced (one instruction per element) and canonicalises its elements when that maximum reaches
+// nb_c_canon_trigger (= 2^32 - 1; the tests lower it to 0 to drive the rare path on every task).
+#ifndef NB_LAZY_CANON
+#define NB_LAZY_CANON 1
+#endif
+#if defined(__CUDACC__)
+__constant__ u32 nb_c_canon_trigger = 0xffffffffu;
+#endif
+NB_HD bool canon_needed(u32 hmax)
+{
+#if defined(__CUDA_ARCH__)
+    return hmax >= nb_c_canon_trigger;
+#else
+    return hmax == 0xffffffffu;
+#endif
+}
+NB_HD u32 umax32(u32 a, u32 b) { return a > b ? a : b; }
+
 constexpr int ROW_STRIDE = 66;                    // u64 per row (64 + 2 padding)
 constexpr int POLY_STRIDE = 16 * ROW_STRIDE;      // u64 per work polynomial
 
@@ -80,10 +102,22 @@ NB_HD void ld2_global(const u64 *p, u64 &x, u64 &y)
     x = p[0]; y = p[1];
 #endif
 }
+#ifndef NB_ST2_SPLIT
+#define NB_ST2_SPLIT 0
+#endif
 NB_HD void st2(u64 *p, u64 x, u64 y)
 {
 #if defined(__CUDA_ARCH__)
+#if NB_ST2_SPLIT
+    // Experiment (profiles/r2_variants.md): two 64-bit stores instead of one 128-bit store, whose four registers must
+    // form an aligned quad -- ptxas pays 4 register moves per store to line up the two field elements.  151 fewer
+    // IMAD.MOV, 56 more STS per step; measured 84.4 ms against 83.8 ms per 4096 bootstraps, so it stays off.
+    // (inline asm: the compiler's load / store vectoriser would fuse two plain stores back into one)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.u64 [%0], %1;\n\tst.volatile.shared.u64 [%0 + 8], %2;" ::"r"(a), "l"(x), "l"(y) : "memory");
+#else
     *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(x, y);
+#endif
 #else
     p[0] = x; p[1] = y;
 #endif
@@ -121,6 +155,51 @@ NB_HD i32 rotate_minus_one(const i32 *acc, int idx, int ar, bool flip)
     return (i32)((neg ? 0u - (u32)src : (u32)src) - (u32)acc[idx]);
 }
 
+// w[r * ROW_STRIDE] = v[r] * twd[r * 64], r = 0..15: the general multiplication that ends the first forward pass
+NB_HD void store_twiddled(const u64 *v, u64 *w, const u64 *twd)
+{
+#if NB_LAZY_CANON
+    u32 hmax = 0;
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        const u64 x = ff_mul_nc(v[r], twd[r * 64]);
+        hmax = umax32(hmax, hi32(x));
+        w[r * ROW_STRIDE] = x;
+    });
+    if (canon_needed(hmax)) {                              // rare: this thread's own 16 elements, before the barrier
+        static_for<0, 16>([&](auto R) {
+            constexpr int r = decltype(R)::value;
+            w[r * ROW_STRIDE] = ff_canon_almost(w[r * ROW_STRIDE]);
+        });
+    }
+#else
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        w[r * ROW_STRIDE] = ff_mul(v[r], twd[r * 64]);
+    });
+#endif
+}
+// v[r] = w[r * ROW_STRIDE] * twd[r * 64]: the general multiplication that opens the last inverse pass
+NB_HD void load_twiddled(u64 *v, const u64 *w, const u64 *twd)
+{
+#if NB_LAZY_CANON
+    u32 hmax = 0;
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        v[r] = ff_mul_nc(w[r * ROW_STRIDE], twd[r * 64]);
+        hmax = umax32(hmax, hi32(v[r]));
+    });
+    if (canon_needed(hmax)) {
+        static_for<0, 16>([&](auto R) { v[decltype(R)::value] = ff_canon_almost(v[decltype(R)::value]); });
+    }
+#else
+    static_for<0, 16>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+        v[r] = ff_mul(w[r * ROW_STRIDE], twd[r * 64]);
+    });
+#endif
+}
+
 // ---- fwd1: task = (poly p, j2); reads ACC, writes W[p][row][col(j2)] -------------------------------
 // twd: forward table [row][j2] (64 per row).  ROTATE=false: digits of acc itself (plain external product).
 template <bool ROTATE>
@@ -141,10 +220,7 @@ NB_HD void phase_fwd1(int task, const i32 *acc_all, u64 *w_all, const u64 *twd, 
     });
     dif_inlane<4, 12, 0>(v);
     u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
-    static_for<0, 16>([&](auto R) {
-        constexpr int r = decltype(R)::value;
-        w[r * ROW_STRIDE] = ff_mul(v[r], twd[r * 64 + j2]);
-    });
+    store_twiddled(v, w, twd + j2);
 }
 
 // ---- fwd2 / inv2: task = (poly p, row, g); 16 elements (a, e), b = 4 g + e ---------------------------
@@ -272,6 +348,28 @@ template <int CT> NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64
             constexpr int d = decltype(D)::value;        // d = mi * 2 + j
             ld2(w + d * POLY_STRIDE, f[d][0], f[d][1]);
         });
+#if NB_LAZY_CANON
+        u64 o[2][2];
+        u32 hmax = 0;
+        static_for<0, 2>([&](auto MO) {
+            constexpr int mo = decltype(MO)::value;
+            static_for<0, 2>([&](auto X) {
+                constexpr int x = decltype(X)::value;
+                const u64 fa[4] = {f[0][x], f[1][x], f[2][x], f[3][x]};
+                const u64 ba[4] = {bk[0 * 2 + mo][x], bk[1 * 2 + mo][x], bk[2 * 2 + mo][x], bk[3 * 2 + mo][x]};
+                o[mo][x] = ff_dot4_sub_nc(fa, ba, bk[8 + mo][x]);
+                hmax = umax32(hmax, hi32(o[mo][x]));
+            });
+        });
+        if (canon_needed(hmax)) {
+            static_for<0, 4>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                o[i >> 1][i & 1] = ff_canon_almost(o[i >> 1][i & 1]);
+            });
+        }
+        st2(w, o[0][0], o[0][1]);
+        st2(w + POLY_STRIDE, o[1][0], o[1][1]);
+#else
         static_for<0, 2>([&](auto MO) {
             constexpr int mo = decltype(MO)::value;
             u64 o[2];
@@ -283,6 +381,7 @@ template <int CT> NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64
             });
             st2(w + mo * POLY_STRIDE, o[0], o[1]);
         });
+#endif
     }
 }
 
@@ -301,10 +400,7 @@ NB_HD void phase_inv1(int task, i32 *acc_all, const u64 *w_all, const u64 *twd_i
     const int ct = pp >> 1, mo = pp & 1;
     const u64 *w = w_all + (ct * 4 + mo) * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     u64 v[16];
-    static_for<0, 16>([&](auto R) {
-        constexpr int r = decltype(R)::value;
-        v[r] = ff_mul(w[r * ROW_STRIDE], twd_inv[r * 64 + j2]);
-    });
+    load_twiddled(v, w, twd_inv + j2);
     dit_inlane<4, 12, 0>(v);
     i32 *acc = acc_all + (ct * 2 + mo) * NTT_N;
     static_for<0, 16>([&](auto J) {
@@ -344,10 +440,7 @@ NB_HD void phase_fwd1_generic(int task, const u64 *x /* 16 values, x[j1] = in[64
     });
     dif_inlane<4, 12, 0>(v);
     u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
-    static_for<0, 16>([&](auto R) {
-        constexpr int r = decltype(R)::value;
-        w[r * ROW_STRIDE] = ff_mul(v[r], twd[r * 64 + j2]);
-    });
+    store_twiddled(v, w, twd + j2);
 }
 // first pass with Torus32 inputs (i32_conversion): the conversion and the twist are one step (ff_twist_i32)
 NB_HD void phase_fwd1_i32(int task, const i32 *x /* 16 values, x[j1] = in[64 j1 + j2] */, u64 *w_all, const u64 *twd)
@@ -360,10 +453,7 @@ NB_HD void phase_fwd1_i32(int task, const i32 *x /* 16 values, x[j1] = in[64 j1 
     });
     dif_inlane<4, 12, 0>(v);
     u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
-    static_for<0, 16>([&](auto R) {
-        constexpr int r = decltype(R)::value;
-        w[r * ROW_STRIDE] = ff_mul(v[r], twd[r * 64 + j2]);
-    });
+    store_twiddled(v, w, twd + j2);
 }
 // last inverse pass with generic outputs: y[j1] = out[64 j1 + j2], almost-canonical ([0, p])
 NB_HD void phase_inv1_generic(int task, u64 *y, const u64 *w_all, const u64 *twd_inv)
@@ -371,10 +461,7 @@ NB_HD void phase_inv1_generic(int task, u64 *y, const u64 *w_all, const u64 *twd
     const int j2 = task & 63, p = task >> 6;
     const u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     u64 v[16];
-    static_for<0, 16>([&](auto R) {
-        constexpr int r = decltype(R)::value;
-        v[r] = ff_mul(w[r * ROW_STRIDE], twd_inv[r * 64 + j2]);
-    });
+    load_twiddled(v, w, twd_inv + j2);
     dit_inlane<4, 12, 0>(v);
     static_for<0, 16>([&](auto J) {
         constexpr int j1 = decltype(J)::value;
@@ -389,10 +476,7 @@ NB_HD void phase_inv1_i32(int task, i32 *y, const u64 *w_all, const u64 *twd_inv
     const int j2 = task & 63, p = task >> 6;
     const u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     u64 v[16];
-    static_for<0, 16>([&](auto R) {
-        constexpr int r = decltype(R)::value;
-        v[r] = ff_mul(w[r * ROW_STRIDE], twd_inv[r * 64 + j2]);
-    });
+    load_twiddled(v, w, twd_inv + j2);
     dit_inlane<4, 12, 0>(v);
     y[0] = ff_to_i32(v[0]);
     static_for<1, 16>([&](auto J) {

@@ -15,8 +15,16 @@ struct nb_ctx {
     u64 *d_ph_fwd, *d_ph_inv;            // middle-twiddle tables [row][j2] of the transform passes
     u64 *d_ones512;                      // 512 * NTT(all-ones), natural order (bk_prepare)
     int sm_count;
-    int stagger_cycles;
     size_t wide_max;                     // largest batch launched in the wide (1 ciphertext / 256 threads) shape
+    int max_chunks;                      // upper bound on the chunks a chain is cut into (1 = no time slicing)
+    unsigned *d_sched;                   // work-queue state of the fused bootstrap (kernels.cuh: BlindRotateArgs)
+    size_t sched_words;
+    int32_t *d_state;                    // parked accumulators of time-sliced launches
+    size_t state_words;
+    float *d_cv_blocks;                  // block sums of the key-switch variances (split launches)
+    size_t cv_words;
+    int force_chunks;                    // developer knob: chunk count of every multi-wave launch (0 = automatic)
+    int stagger_cycles;                  // start-up offset of the second CTA per SM in single-wave launches
     std::string err;
 };
 
@@ -70,14 +78,28 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
     ctx->device = device;
     ctx->stream = (cudaStream_t)stream;
     ctx->d_ph_fwd = ctx->d_ph_inv = ctx->d_ones512 = nullptr;
+    ctx->d_sched = nullptr; ctx->d_state = nullptr; ctx->sched_words = ctx->state_words = 0;
+    ctx->d_cv_blocks = nullptr; ctx->cv_words = 0;
     *out = ctx;   // returned even on failure so that nb_last_error() can be read; caller destroys it
     NB_ON_DEVICE(ctx);
     cudaDeviceProp prop;
     NB_TRY(check(ctx, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"));
     ctx->sm_count = prop.multiProcessorCount;
     {
-        const char *e = getenv("NUFHE_B200_STAGGER");     // developer knob (cycles); measured: no effect, default off
-        ctx->stagger_cycles = e ? atoi(e) : 0;
+        const char *e = getenv("NUFHE_B200_MAX_CHUNKS");  // developer knob: 1 disables the time slicing of chains
+        ctx->max_chunks = e ? atoi(e) : 50;
+        if (ctx->max_chunks < 1) ctx->max_chunks = 1;
+        e = getenv("NUFHE_B200_FORCE_CHUNKS");
+        ctx->force_chunks = e ? atoi(e) : 0;
+        e = getenv("NUFHE_B200_STAGGER");
+        ctx->stagger_cycles = e ? atoi(e) : 24000;        // about half a CMux step of the throughput shape
+    }
+    if (const char *e = getenv("NUFHE_B200_FORCE_RARE_PATH")) {
+        // test knob: run the canonicalisation fix-up of the deferred-canonicalisation phases on every task
+        if (atoi(e)) {
+            const u32 zero = 0;
+            NB_TRY(check(ctx, cudaMemcpyToSymbol(nb_c_canon_trigger, &zero, sizeof(zero)), "cudaMemcpyToSymbol"));
+        }
     }
     if (prop.major < 10)
         return fail(ctx, NB_EUNSUPPORTED, "libnufhe_b200 is built for sm_100a only; device is sm_" +
@@ -95,12 +117,14 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
                                            (int)br_smem_bytes<BrWide>()), "cudaFuncSetAttribute(blind_rotate wide)"));
     {   // batches that fit one wave of wide CTAs (one ciphertext on 256 threads) take the low-latency shape
         const char *e = getenv("NUFHE_B200_WIDE_MAX");
-        ctx->wide_max = e ? (size_t)atoll(e) : (size_t)ctx->sm_count * BrWide::CTAS_PER_SM;
+        // up to one wave the wide shape has the shortest step; between one and ~1.7 waves it still wins, time-sliced
+        // over all SMs, against a throughput-shape launch that leaves half of the SMs with one CTA (r2 sweep)
+        ctx->wide_max = e ? (size_t)atoll(e) : (size_t)ctx->sm_count * BrWide::CTAS_PER_SM * 17 / 10;
     }
-    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
-    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
-    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
-    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_inverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTTK_SMEM_BYTES), "attr"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_I32_BYTES)), "attr"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_U64_BYTES)), "attr"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_U64_BYTES)), "attr"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_inverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_U64_BYTES)), "attr"));
     return NB_OK;
 }
 
@@ -111,6 +135,9 @@ void nb_ctx_destroy(nb_ctx *ctx)
     if (ctx->d_ph_fwd) cudaFree(ctx->d_ph_fwd);
     if (ctx->d_ph_inv) cudaFree(ctx->d_ph_inv);
     if (ctx->d_ones512) cudaFree(ctx->d_ones512);
+    if (ctx->d_sched) cudaFree(ctx->d_sched);
+    if (ctx->d_state) cudaFree(ctx->d_state);
+    if (ctx->d_cv_blocks) cudaFree(ctx->d_cv_blocks);
     delete ctx;
 }
 
@@ -161,7 +188,7 @@ int nb_ntt_forward_i32(nb_ctx *ctx, const int32_t *in, uint64_t *out, size_t bat
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_i32: null argument");
     NB_ON_DEVICE(ctx);
-    ntt_forward_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
+    ntt_forward_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, ntt_smem_bytes(NTT_RAW_I32_BYTES), ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<i32>");
 }
 
@@ -171,7 +198,7 @@ int nb_ntt_forward_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_u64: null argument");
     NB_ON_DEVICE(ctx);
-    ntt_forward_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
+    ntt_forward_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, ntt_smem_bytes(NTT_RAW_U64_BYTES), ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<u64>");
 }
 
@@ -181,7 +208,7 @@ int nb_ntt_inverse_i32(nb_ctx *ctx, const uint64_t *in, int32_t *out, size_t bat
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_i32: null argument");
     NB_ON_DEVICE(ctx);
-    ntt_inverse_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
+    ntt_inverse_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, ntt_smem_bytes(NTT_RAW_U64_BYTES), ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<i32>");
 }
 
@@ -191,7 +218,7 @@ int nb_ntt_inverse_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_u64: null argument");
     NB_ON_DEVICE(ctx);
-    ntt_inverse_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, NTTK_SMEM_BYTES, ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
+    ntt_inverse_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, ntt_smem_bytes(NTT_RAW_U64_BYTES), ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<u64>");
 }
 
@@ -222,19 +249,72 @@ int nb_bk_prepare(nb_ctx *ctx, const uint64_t *bk_ref, uint64_t *bk_int, size_t 
     return launch_check(ctx, "bk_prepare_kernel");
 }
 
-// One launch of the fused kernel in the shape that suits the batch: up to one wave of "wide" CTAs (1 ciphertext on
-// 256 threads, shortest step) for small batches, else 2 ciphertexts per CTA (highest throughput).
-static void launch_br(nb_ctx *ctx, const BlindRotateArgs &p)
+}  // extern "C"
+
+// Chunks per chain for `chains` chains on `slots` resident CTAs (kernels.cuh: blind_rotate_kernel).  One wave or
+// less needs no slicing.  Otherwise the launch takes ceil(chains * C / slots) rounds of ceil(n / C) steps; each chunk
+// also pays for parking / fetching the accumulators and refilling the pipeline (about a third of a step).
+static int pick_chunks(size_t chains, size_t slots, int n, int max_chunks)
 {
-    if (p.batch <= ctx->wide_max) {
-        blind_rotate_kernel<BrWide><<<(int)p.batch, BrWide::THREADS, br_smem_bytes<BrWide>(), ctx->stream>>>(
-            p, ctx->d_ph_fwd, ctx->d_ph_inv);
-    } else {
-        const int grid = (int)((p.batch + BrDefault::CT - 1) / BrDefault::CT);
-        blind_rotate_kernel<BrDefault><<<grid, BrDefault::THREADS, br_smem_bytes<BrDefault>(), ctx->stream>>>(
-            p, ctx->d_ph_fwd, ctx->d_ph_inv);
+    if (chains <= slots || n <= 1 || max_chunks <= 1) return 1;
+    int best = 1;
+    double best_cost = 0;
+    for (int c = 1; c <= max_chunks && c <= n / 8; c++) {
+        const int steps = (n + c - 1) / c;
+        const int chunks = (n + steps - 1) / steps;
+        const double rounds = (double)((chains * (size_t)chunks + slots - 1) / slots);
+        const double cost = rounds * (steps + 0.35);
+        if (c == 1 || cost < best_cost * 0.995) { best = chunks; best_cost = cost; }
     }
+    return best;
 }
+
+static int reserve_words(nb_ctx *ctx, void **buf, size_t *have, size_t want, size_t elem)
+{
+    if (*have >= want) return NB_OK;
+    if (*buf) NB_TRY(check(ctx, cudaFree(*buf), "cudaFree"));
+    *buf = nullptr; *have = 0;
+    const size_t grow = want + want / 4;
+    NB_TRY(check(ctx, cudaMalloc(buf, grow * elem), "cudaMalloc(work queue)"));
+    *have = grow;
+    return NB_OK;
+}
+
+template <class Cfg> static int launch_br_cfg(nb_ctx *ctx, BlindRotateArgs &p)
+{
+    const size_t slots = (size_t)ctx->sm_count * Cfg::CTAS_PER_SM;
+    const size_t chains = (p.batch + Cfg::CT - 1) / Cfg::CT;
+    int chunks = p.plain ? 1 : pick_chunks(chains, slots, p.n, ctx->max_chunks);
+    if (!p.plain && ctx->force_chunks > 0 && chains > slots) chunks = ctx->force_chunks < p.n ? ctx->force_chunks : p.n;
+    p.chains = (unsigned)chains;
+    p.steps_per_chunk = p.plain ? 1 : (p.n + chunks - 1) / chunks;
+    chunks = p.plain ? 1 : (p.n + p.steps_per_chunk - 1) / p.steps_per_chunk;
+    p.chunks = (unsigned)chunks;
+    p.sched = nullptr; p.state = nullptr;
+    p.sm_count = ctx->sm_count; p.stagger_cycles = ctx->stagger_cycles;
+    size_t grid = chains;
+    if (chains > slots) {
+        // more than one wave: persistent CTAs pull (chain, chunk) tickets
+        NB_TRY(reserve_words(ctx, (void **)&ctx->d_sched, &ctx->sched_words, BR_SCHED_HEADER + chains, sizeof(unsigned)));
+        if (chunks > 1)
+            NB_TRY(reserve_words(ctx, (void **)&ctx->d_state, &ctx->state_words, chains * Cfg::CT * 2 * NTT_N, sizeof(int32_t)));
+        NB_TRY(check(ctx, cudaMemsetAsync(ctx->d_sched, 0, (BR_SCHED_HEADER + chains) * sizeof(unsigned), ctx->stream), "cudaMemsetAsync"));
+        p.sched = ctx->d_sched; p.state = ctx->d_state;
+        grid = slots;
+    }
+    blind_rotate_kernel<Cfg><<<(int)grid, Cfg::THREADS, br_smem_bytes<Cfg>(), ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);
+    return NB_OK;
+}
+
+// One launch of the fused kernel in the shape that suits the batch: "wide" CTAs (1 ciphertext on 256 threads,
+// shortest step) while the batch fits one wave of them, else 2 ciphertexts per CTA (highest throughput).
+static int launch_br(nb_ctx *ctx, BlindRotateArgs &p)
+{
+    if (p.batch <= ctx->wide_max) return launch_br_cfg<BrWide>(ctx, p);
+    return launch_br_cfg<BrDefault>(ctx, p);
+}
+
+extern "C" {
 
 int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, size_t bk_row, size_t batch)
 {
@@ -243,8 +323,8 @@ int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, siz
     NB_ON_DEVICE(ctx);
     BlindRotateArgs p{};
     p.accum = accum; p.accum_out = accum; p.bk = (const u64 *)bk_int + bk_row * BK_ROW_U64;
-    p.plain = 1; p.batch = batch; p.sm_count = ctx->sm_count; p.stagger_cycles = 0;
-    launch_br(ctx, p);
+    p.plain = 1; p.batch = batch;
+    NB_TRY(launch_br(ctx, p));
     return launch_check(ctx, "blind_rotate_kernel(plain external product)");
 }
 
@@ -253,9 +333,7 @@ static int launch_blind_rotate(nb_ctx *ctx, BlindRotateArgs &p)
     if (p.n <= 0 || p.n > LWE_N_MAX) return fail(ctx, NB_EUNSUPPORTED, "LWE dimension out of range");
     if (p.batch == 0) return NB_OK;
     NB_ON_DEVICE(ctx);
-    p.sm_count = ctx->sm_count;
-    p.stagger_cycles = ctx->stagger_cycles;
-    launch_br(ctx, p);
+    NB_TRY(launch_br(ctx, p));
     return launch_check(ctx, "blind_rotate_kernel");
 }
 
@@ -335,7 +413,15 @@ int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, cons
             NB_TRY(check(ctx, cudaMemsetAsync(res_a, 0, batch * n * sizeof(int32_t), ctx->stream), "cudaMemsetAsync"));
             NB_TRY(check(ctx, cudaMemsetAsync(res_b, 0, batch * sizeof(int32_t), ctx->stream), "cudaMemsetAsync"));
         }
+        if (splits > 1 && res_cv) {
+            NB_TRY(reserve_words(ctx, (void **)&ctx->d_cv_blocks, &ctx->cv_words, batch * KS_CV_BLOCKS, sizeof(float)));
+            p.cv_blocks = ctx->d_cv_blocks;
+        }
         keyswitch_kernel<<<dim3(grid, splits), KS_THREADS, KS_SMEM_BYTES, ctx->stream>>>(p);
+        if (p.cv_blocks) {
+            NB_TRY(launch_check(ctx, "keyswitch_kernel"));
+            ks_cv_finalize_kernel<<<(int)((batch + 127) / 128), 128, 0, ctx->stream>>>(res_cv, p.cv_blocks, batch);
+        }
     } else {
         keyswitch_generic_kernel<<<(int)batch, 512, 0, ctx->stream>>>(p);
     }
@@ -454,6 +540,36 @@ int nb_lwe_affine(nb_ctx *ctx, int32_t *res_a, int32_t *res_b, const int32_t *x1
     lwe_affine_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
         res_a, res_b, x1_a, x1_b, x2_a, x2_b, c, s1, s2, batch, (int)n);
     return launch_check(ctx, "lwe_affine_kernel");
+}
+
+int nb_lwe_dot(nb_ctx *ctx, int32_t *out, const int32_t *a, const int32_t *key, const int32_t *add1,
+               const int32_t *add2, int32_t sign, size_t batch, size_t n)
+{
+    if (!ctx) return NB_EINVAL;
+    if (!out || !a || !key) return fail(ctx, NB_EINVAL, "nb_lwe_dot: null argument");
+    if (n == 0 || n > (1u << 30)) return fail(ctx, NB_EINVAL, "nb_lwe_dot: bad LWE dimension");
+    if (batch == 0) return NB_OK;
+    NB_ON_DEVICE(ctx);
+    size_t blocks = (batch * 32 + 255) / 256, cap = (size_t)ctx->sm_count * 16;
+    lwe_dot_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(out, a, key, add1, add2, sign, batch, (int)n);
+    return launch_check(ctx, "lwe_dot_kernel");
+}
+
+int nb_make_keyswitch_key(nb_ctx *ctx, int32_t *ks_a, int32_t *ks_b, float *ks_cv, const int32_t *in_key,
+                          const int32_t *out_key, const int32_t *noises_a, const int32_t *noises_b, size_t in_size,
+                          size_t n, int t, int log2_base, float noise_variance)
+{
+    if (!ctx) return NB_EINVAL;
+    if (!ks_a || !ks_b || !ks_cv || !in_key || !out_key || !noises_a || !noises_b)
+        return fail(ctx, NB_EINVAL, "nb_make_keyswitch_key: null argument");
+    if (t < 1 || log2_base < 1 || t * log2_base > 31 || n == 0) return fail(ctx, NB_EINVAL, "nb_make_keyswitch_key: bad decomposition");
+    if (in_size == 0) return NB_OK;
+    NB_ON_DEVICE(ctx);
+    const size_t rows = in_size * (size_t)t << log2_base;
+    size_t blocks = (rows * 32 + 255) / 256, cap = (size_t)ctx->sm_count * 16;
+    make_keyswitch_key_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
+        ks_a, ks_b, ks_cv, in_key, out_key, noises_a, noises_b, in_size, (int)n, t, log2_base, noise_variance);
+    return launch_check(ctx, "make_keyswitch_key_kernel");
 }
 
 }  // extern "C"

@@ -196,7 +196,10 @@ NB_D u64 ff_canon_dev(u32 v0, u32 v1)
 // l + (m + h0) phi - (h0 + h1); the carry c of mu = m + h0 is c phi^2 = c phi - c, and mu + c cannot overflow
 // (c = 1 implies mu <= 2^32 - 2), so it is the 64-bit difference  ((mu + c) : l) - (h0 + h1 + c)  >= -2^33 - 1,
 // one borrow fix (as in ff_sub) and one conditional subtraction of p.
-NB_D u64 ff_reduce_limbs(u32 l, u32 m, u32 h0, u32 h1)
+// _nc ("not canonicalised"): the 64-bit value after the borrow fix -- the right residue, but anywhere in [0, 2^64).
+// It exceeds p with probability 2^-32; callers that skip the conditional subtraction watch the high limbs instead
+// (hi == 2^32 - 1 is necessary for v >= p - 1) and canonicalise on that rare path (br_phases.cuh).
+NB_D u64 ff_reduce_limbs_nc(u32 l, u32 m, u32 h0, u32 h1)
 {
     u32 r0, r1, d0, d1, k;
     asm("add.cc.u32 %1, %6, %7;\n\t"         // mu = m + h0
@@ -211,9 +214,24 @@ NB_D u64 ff_reduce_limbs(u32 l, u32 m, u32 h0, u32 h1)
         "addc.u32 %1, %1, %4;"
         : "=&r"(r0), "=&r"(r1), "=&r"(d0), "=&r"(d1), "=&r"(k)
         : "r"(l), "r"(m), "r"(h0), "r"(h1));
-    return ff_canon_dev(r0, r1);
+    return pack(r0, r1);
+}
+NB_D u64 ff_reduce_limbs(u32 l, u32 m, u32 h0, u32 h1)
+{
+    const u64 v = ff_reduce_limbs_nc(l, m, h0, h1);
+    return ff_canon_dev(lo32(v), hi32(v));
 }
 #endif
+
+// [0, p] form of any 64-bit value: the rare-path fix of the _nc results
+NB_HD u64 ff_canon_almost(u64 v)
+{
+#if defined(__CUDA_ARCH__)
+    return ff_canon_dev(lo32(v), hi32(v));
+#else
+    return ff_canon(v);
+#endif
+}
 
 NB_HD u64 ff_mul(u64 a, u64 b)
 {
@@ -224,6 +242,18 @@ NB_HD u64 ff_mul(u64 a, u64 b)
 #else
     unsigned __int128 pr = (unsigned __int128)a * b;
     return ff_reduce128((u64)pr, (u64)(pr >> 64));
+#endif
+}
+
+// a * b as the right residue in [0, 2^64) on the device (see ff_reduce_limbs_nc); canonical on the host
+NB_HD u64 ff_mul_nc(u64 a, u64 b)
+{
+#if defined(__CUDA_ARCH__)
+    u32 l, m, h0, h1;
+    mul128(a, b, l, m, h0, h1);
+    return ff_reduce_limbs_nc(l, m, h0, h1);
+#else
+    return ff_mul(a, b);
 #endif
 }
 
@@ -248,6 +278,21 @@ NB_HD u64 ff_dot4(const u64 *a, const u64 *b)
     }
     u64 lo = (u64)acc, hi = (u64)(acc >> 64);
     return ff_sub(ff_reduce128(lo, hi), (u64)c << 32);
+#endif
+}
+
+// the same dot product minus a canonical c, as a residue in [0, 2^64) on the device: ff_sub keeps any 64-bit
+// minuend correct mod p (it only adds p back on a borrow), so the two subtractions need no canonical input
+NB_HD u64 ff_dot4_sub_nc(const u64 *a, const u64 *b, u64 c)
+{
+#if defined(__CUDA_ARCH__)
+    u32 c0, c1, c2, c3, c4 = 0;
+    mul128(a[0], b[0], c0, c1, c2, c3);
+#pragma unroll
+    for (int k = 1; k < 4; k++) mac128(a[k], b[k], c0, c1, c2, c3, c4);
+    return ff_sub(ff_sub(ff_reduce_limbs_nc(c0, c1, c2, c3), (u64)c4 << 32), c);
+#else
+    return ff_sub(ff_dot4(a, b), c);
 #endif
 }
 

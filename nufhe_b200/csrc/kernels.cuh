@@ -19,35 +19,87 @@
 namespace nb {
 
 constexpr int LWE_N_MAX = 1024;          // upper bound on the LWE dimension n handled by the gate kernels
+
+NB_D u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+NB_D void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+NB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> NB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- stand-alone batched transforms (reference: transform/computation.mako `standalone_transform`) ---
 // natural order in and out.  Same three passes as the fused bootstrap (br_phases.cuh), 4 polynomials per
-// sweep of 256 threads, 2 CTAs per SM; the natural-order side is read / written with coalesced 128-byte
-// warp accesses and the re-ordering happens in shared memory.
-constexpr size_t NTTK_SMEM_BYTES = (size_t)NTT_SWEEP_POLYS * POLY_STRIDE * sizeof(u64) + NTT_N * sizeof(u64);
+// sweep of 256 threads, 2 persistent CTAs per SM.  The natural-order side never meets the arithmetic directly:
+//   * the next sweep's input is fetched with cp.async (16 bytes per request) into a second staging buffer while the
+//     current sweep computes, so no pass waits on global memory;
+//   * a thread owns the natural-order pairs (2t, 2t+1) and (2t+512, 2t+513) of every polynomial: in the pass layout
+//     those four elements sit in two 16-byte shared-memory words 8 rows apart (ntt_pair_position), so the u64 side is
+//     moved with 128-bit shared AND 128-bit global accesses (512 contiguous bytes per warp), bank-conflict free;
+//   * the int32 side is read from / written to global memory as 128-byte warp rows (x[64 j1 + j2], lanes = j2).
+constexpr int NTT_RAW_I32_BYTES = NTT_SWEEP_POLYS * NTT_N * (int)sizeof(i32);
+constexpr int NTT_RAW_U64_BYTES = NTT_SWEEP_POLYS * NTT_N * (int)sizeof(u64);
+constexpr size_t ntt_smem_bytes(int raw_bytes)
+{
+    return (size_t)NTT_SWEEP_POLYS * POLY_STRIDE * sizeof(u64) + NTT_N * sizeof(u64) + 2 * (size_t)raw_bytes;
+}
+
+// shared-memory position (in u64) of natural element k = 2 t of a polynomial, t = threadIdx.x in [0, 256): the
+// elements 2t+1, 2t+512 and 2t+513 are at +8 rows, +1 and +8 rows +1 (k1 = k % 16 is even, so brev4(k1 + 1) =
+// brev4(k1) + 8; adding 512 to k sets the top bit of k2 >> 2, i.e. bit 0 of the stored column index)
+NB_D int ntt_pair_position(int t)
+{
+    const int row = brev(2 * (t & 7), 4), u = brev((t >> 3) & 3, 2), i0 = brev(t >> 5, 4);
+    return row * ROW_STRIDE + col_of(u, i0);
+}
+NB_D u64 ff_zero_if_p(u64 x) { return x == FF_P ? 0 : x; }       // [0, p] -> canonical
+
+// stage one sweep (4 polynomials, clamped at the end of the batch) with 16-byte cp.async requests
+template <int POLY_BYTES> NB_D void ntt_stage(unsigned char *raw, const unsigned char *in, size_t p0, size_t batch, int tid)
+{
+    constexpr int CHUNKS = POLY_BYTES / 16;
+#pragma unroll
+    for (int pl = 0; pl < NTT_SWEEP_POLYS; pl++) {
+        const size_t p = min(p0 + pl, batch - 1);
+        for (int c = tid; c < CHUNKS; c += NTT_SWEEP_THREADS)
+            cp_async16(raw + pl * POLY_BYTES + c * 16, in + p * POLY_BYTES + (size_t)c * 16);
+    }
+}
 
 template <bool IN_I32>
 __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_forward_kernel(const void *__restrict__ in, u64 *__restrict__ out,
                                                                             const u64 *__restrict__ twd_g, size_t batch)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int POLY_BYTES = NTT_N * (IN_I32 ? 4 : 8), RAW_BYTES = NTT_SWEEP_POLYS * POLY_BYTES;
     u64 *w = reinterpret_cast<u64 *>(smem_raw);
     u64 *twd = w + NTT_SWEEP_POLYS * POLY_STRIDE;
+    unsigned char *raw = reinterpret_cast<unsigned char *>(twd + NTT_N);
     const int tid = threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * NTT_SWEEP_POLYS;
+    size_t p0 = (size_t)blockIdx.x * NTT_SWEEP_POLYS;
+    if (p0 < batch) ntt_stage<POLY_BYTES>(raw, (const unsigned char *)in, p0, batch, tid);
+    cp_async_commit();
     for (int i = tid; i < NTT_N; i += NTT_SWEEP_THREADS) twd[i] = twd_g[i];
-    __syncthreads();
-    for (size_t p0 = (size_t)blockIdx.x * NTT_SWEEP_POLYS; p0 < batch; p0 += (size_t)gridDim.x * NTT_SWEEP_POLYS) {
-        {   // pass 1: thread = (poly, j2), reads x[64 j1 + j2]
+    const int pos = ntt_pair_position(tid);
+    int buf = 0;
+    for (; p0 < batch; p0 += stride, buf ^= 1) {
+        if (p0 + stride < batch) ntt_stage<POLY_BYTES>(raw + (buf ^ 1) * RAW_BYTES, (const unsigned char *)in, p0 + stride, batch, tid);
+        cp_async_commit();
+        cp_async_wait<1>();                       // everything but the group just committed has landed
+        __syncthreads();
+        {   // pass 1: thread = (poly, j2), reads x[64 j1 + j2] from the staging buffer
             const int pl = tid >> 6, j2 = tid & 63;
-            const size_t p = min(p0 + pl, batch - 1);
+            const unsigned char *src = raw + buf * RAW_BYTES + pl * POLY_BYTES;
             if (IN_I32) {
                 i32 x[16];
 #pragma unroll
-                for (int j1 = 0; j1 < 16; j1++) x[j1] = ((const i32 *)in)[p * NTT_N + 64 * j1 + j2];
+                for (int j1 = 0; j1 < 16; j1++) x[j1] = reinterpret_cast<const i32 *>(src)[64 * j1 + j2];
                 phase_fwd1_i32(tid, x, w, twd);
             } else {
                 u64 x[16];
 #pragma unroll
-                for (int j1 = 0; j1 < 16; j1++) x[j1] = ff_canon(((const u64 *)in)[p * NTT_N + 64 * j1 + j2]);
+                for (int j1 = 0; j1 < 16; j1++) x[j1] = ff_canon(reinterpret_cast<const u64 *>(src)[64 * j1 + j2]);
                 phase_fwd1_generic(tid, x, w, twd);
             }
         }
@@ -56,40 +108,52 @@ __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_forward_kernel(const
         __syncthreads();
         { const int u = tid & 3, r = (tid >> 2) & 15, p = tid >> 6; phase_fwd3(p, r, u, w); }
         __syncthreads();
-        // natural-order store: thread handles k = tid + 256 e of each polynomial
+        // natural-order store: 16 bytes = elements (2t, 2t+1) and (2t+512, 2t+513) of each polynomial
 #pragma unroll
         for (int pl = 0; pl < NTT_SWEEP_POLYS; pl++) {
             if (p0 + pl < batch) {
-#pragma unroll
-                for (int e = 0; e < NTT_N / NTT_SWEEP_THREADS; e++) {
-                    const int k = tid + NTT_SWEEP_THREADS * e;
-                    out[(p0 + pl) * NTT_N + k] = ff_canon(w[pl * POLY_STRIDE + w_position_of_natural(k)]);
-                }
+                u64 a0, a1, b0, b1;
+                ld2(w + pl * POLY_STRIDE + pos, a0, a1);                       // k = 2t, 2t + 512
+                ld2(w + pl * POLY_STRIDE + pos + 8 * ROW_STRIDE, b0, b1);      // k = 2t + 1, 2t + 513
+                ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out + (p0 + pl) * NTT_N);
+                dst[tid] = make_ulonglong2(ff_zero_if_p(a0), ff_zero_if_p(b0));
+                dst[tid + 256] = make_ulonglong2(ff_zero_if_p(a1), ff_zero_if_p(b1));
             }
         }
         __syncthreads();
     }
+    cp_async_wait<0>();
 }
 
 template <bool OUT_I32>
 __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_inverse_kernel(const u64 *__restrict__ in, void *__restrict__ out,
                                                                             const u64 *__restrict__ twd_g, size_t batch)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int POLY_BYTES = NTT_N * 8, RAW_BYTES = NTT_SWEEP_POLYS * POLY_BYTES;
     u64 *w = reinterpret_cast<u64 *>(smem_raw);
     u64 *twd = w + NTT_SWEEP_POLYS * POLY_STRIDE;
+    unsigned char *raw = reinterpret_cast<unsigned char *>(twd + NTT_N);
     const int tid = threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * NTT_SWEEP_POLYS;
+    size_t p0 = (size_t)blockIdx.x * NTT_SWEEP_POLYS;
+    if (p0 < batch) ntt_stage<POLY_BYTES>(raw, (const unsigned char *)in, p0, batch, tid);
+    cp_async_commit();
     for (int i = tid; i < NTT_N; i += NTT_SWEEP_THREADS) twd[i] = twd_g[i];
-    __syncthreads();
-    for (size_t p0 = (size_t)blockIdx.x * NTT_SWEEP_POLYS; p0 < batch; p0 += (size_t)gridDim.x * NTT_SWEEP_POLYS) {
+    const int pos = ntt_pair_position(tid);
+    int buf = 0;
+    for (; p0 < batch; p0 += stride, buf ^= 1) {
+        if (p0 + stride < batch) ntt_stage<POLY_BYTES>(raw + (buf ^ 1) * RAW_BYTES, (const unsigned char *)in, p0 + stride, batch, tid);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        // natural order -> pass layout (the mirror image of the forward kernel's store), canonicalising on the way
 #pragma unroll
         for (int pl = 0; pl < NTT_SWEEP_POLYS; pl++) {
-            const size_t p = min(p0 + pl, batch - 1);
-#pragma unroll
-            for (int e = 0; e < NTT_N / NTT_SWEEP_THREADS; e++) {
-                const int k = tid + NTT_SWEEP_THREADS * e;
-                w[pl * POLY_STRIDE + w_position_of_natural(k)] = ff_canon(in[p * NTT_N + k]);
-            }
+            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(raw + buf * RAW_BYTES + pl * POLY_BYTES);
+            const ulonglong2 lo = src[tid], hi = src[tid + 256];
+            st2(w + pl * POLY_STRIDE + pos, ff_canon(lo.x), ff_canon(hi.x));
+            st2(w + pl * POLY_STRIDE + pos + 8 * ROW_STRIDE, ff_canon(lo.y), ff_canon(hi.y));
         }
         __syncthreads();
         { const int u = tid & 3, r = (tid >> 2) & 15, p = tid >> 6; phase_inv3(p, r, u, w); }
@@ -110,12 +174,13 @@ __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_inverse_kernel(const
                 phase_inv1_generic(tid, y, w, twd);
                 if (p0 + pl < batch) {
 #pragma unroll
-                    for (int j1 = 0; j1 < 16; j1++) ((u64 *)out)[(p0 + pl) * NTT_N + 64 * j1 + j2] = ff_canon(y[j1]);
+                    for (int j1 = 0; j1 < 16; j1++) ((u64 *)out)[(p0 + pl) * NTT_N + 64 * j1 + j2] = ff_zero_if_p(y[j1]);
                 }
             }
         }
         __syncthreads();
     }
+    cp_async_wait<0>();
 }
 
 // ---- element-wise field ops (unit tests of the arithmetic; key generation) ----------------------
@@ -201,10 +266,16 @@ struct BlindRotateArgs {
     int n;                  // LWE dimension (500); n = 0 with `plain` = one external product
     int extract;            // write out_a/out_b
     int plain;              // 1: accum <- bk[0] (x) accum, no rotation (tgsw.py:165-172), n ignored
-    int sm_count;           // for the start-up stagger of co-resident CTAs
-    int stagger_cycles;     // ~ half a CMux step; 0 disables
     size_t batch;
+    // work queue (see blind_rotate_kernel): `chains` groups of Cfg::CT ciphertexts, each cut into `chunks` runs of
+    // `steps_per_chunk` CMux steps.  sched == null: one chain per CTA, no queue (single wave).
+    unsigned *sched;        // [0] = next ticket, [BR_SCHED_HEADER + chain] = chunks of the chain completed so far
+    i32 *state;             // accumulators parked between the chunks of a chain: (chains * CT, 2, 1024)
+    unsigned chains, chunks;
+    int steps_per_chunk;
+    int sm_count, stagger_cycles;   // single-wave launches: the second CTA of every SM starts this much later
 };
+constexpr int BR_SCHED_HEADER = 32;      // the ticket counter has a 128-byte line of its own
 
 struct Br2Smem {
     i32 *acc;      // [CT][2][1024]
@@ -263,80 +334,135 @@ NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *
     if (tid < Cfg::INV_TASKS) phase_inv1<ROTATE>(tid, s.acc, s.w, s.twd_inv);
 }
 
+NB_D unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+NB_D void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// The kernel is persistent: the grid is at most one wave of resident CTAs (Cfg::CTAS_PER_SM per SM) and every CTA
+// pulls work items from a ticket counter until none are left.  A work item is one CHUNK of one CHAIN: a chain is the
+// whole blind rotation of Cfg::CT ciphertexts, a chunk `steps_per_chunk` consecutive CMux steps of it.  Tickets run
+// chunk-major (all first chunks, then all second chunks, ...), so a batch that is not a multiple of the wave size is
+// time-sliced over all SMs instead of leaving a partial last wave: 1024 ciphertexts take 1.73 wave-times instead of
+// 2 (the host picks the chunk count, capi.cu: pick_chunks).  Between chunks the accumulators (8 KB per ciphertext)
+// are parked in global memory; chunk c of a chain waits for the chain's progress counter to reach c -- its
+// predecessor holds a lower ticket, i.e. belongs to a CTA that is already running, so the wait cannot deadlock.
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g,
                                                                        const u64 *__restrict__ twd_inv_g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Br2Smem s = br2_carve<Cfg>(smem_raw);
+    __shared__ unsigned s_item;
     const int tid = threadIdx.x;
     for (int i = tid; i < NTT_N; i += Cfg::THREADS) { s.twd_fwd[i] = twd_fwd_g[i]; s.twd_inv[i] = twd_inv_g[i]; }
-
-    // Two CTAs share an SM (Cfg::CTAS_PER_SM).  Optional start-up stagger so that the pair runs out of phase
-    // (MAC is IMAD-heavy, the transform passes IADD3-heavy).  Measured on B200: no gain -- the kernel sits at
-    // the ALU pipe's ceiling either way (profiles/r1_v23_*) -- so ctx->stagger_cycles defaults to 0.
-    if (Cfg::CTAS_PER_SM > 1 && p.stagger_cycles > 0 && ((blockIdx.x / p.sm_count) & 1) &&
-        blockIdx.x < (unsigned)(Cfg::CTAS_PER_SM * p.sm_count)) {
+    const unsigned total = p.chains * p.chunks;
+    constexpr int ACC_WORDS = Cfg::CT * 2 * NTT_N;
+    // Two CTAs share an SM.  In a single-wave launch they would march through the phases in lock step (the MAC is
+    // multiplier-bound and stalls both integer pipes, the transform passes are adder-bound); started half a step apart
+    // they fill each other's gaps -- what multi-wave launches drift into by themselves (12.3 vs 12.8 ms per wave,
+    // profiles/r2_variants.md).
+    if (Cfg::CTAS_PER_SM > 1 && !p.sched && p.stagger_cycles > 0 && blockIdx.x >= (unsigned)p.sm_count) {
         if (tid == 0) {
             const long long t0 = clock64();
             while (clock64() - t0 < p.stagger_cycles) { }
         }
         __syncthreads();
     }
-    const size_t ct0 = (size_t)blockIdx.x * Cfg::CT;
-    // ciphertext slots beyond the batch replay the last ciphertext and store nothing
-    auto ct_of = [&](int slot) { size_t c = ct0 + slot; return c < p.batch ? c : p.batch - 1; };
 
-    // accumulator initialisation: 8 polynomials x 1024 coefficients
-    for (int e = tid; e < Cfg::CT * 2 * NTT_N; e += Cfg::THREADS) {
-        const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);
-        const size_t c = ct_of(slot);
-        i32 val;
-        if (p.accum) {
-            val = p.accum[(c * 2 + mi) * NTT_N + x];
-        } else {
-            // ACC = (0, X^(2N - barb) * [mu, ..., mu])   (bootstrap.py:177-182, 224)
-            u32 xb;
-            if (p.job_batch && c >= p.job_batch) {
-                const size_t d = c - p.job_batch;
-                xb = (u32)p.j2_c + (u32)p.j2_s1 * (u32)p.j2_in1_b[d] + (p.j2_in2_b ? (u32)p.j2_s2 * (u32)p.j2_in2_b[d] : 0u);
-            } else {
-                xb = (u32)p.c + (u32)p.s1 * (u32)p.in1_b[c] + (p.in2_b ? (u32)p.s2 * (u32)p.in2_b[c] : 0u);
-            }
-            int q = 2 * NTT_N - modswitch_2n((i32)xb);
-            if (q < NTT_N) val = x < q ? (i32)(0u - (u32)p.mu) : p.mu;
-            else val = x < q - NTT_N ? p.mu : (i32)(0u - (u32)p.mu);
-            if (mi == 0) val = 0;
-        }
-        s.acc[e] = val;
-    }
-    if (p.plain) {
-        __syncthreads();
-        br2_step<false, Cfg>(s, p.bk, s.rot, tid);
-        __syncthreads();
-    } else {
-        if (tid < Cfg::CT) s.rot[tid] = br2_rotation(p, ct_of(tid), 0);
-        __syncthreads();
-        for (int i = 0; i < p.n; i++) {
-            int next = 0;
-            if (tid < Cfg::CT && i + 1 < p.n) next = br2_rotation(p, ct_of(tid), i + 1);
-            br2_step<true, Cfg>(s, p.bk + (size_t)i * BK_ROW_U64, s.rot + (i & 1) * Cfg::CT, tid);
-            if (tid < Cfg::CT) s.rot[((i + 1) & 1) * Cfg::CT + tid] = next;
+    for (unsigned item = blockIdx.x;; ) {
+        if (p.sched) {
+            __syncthreads();                                   // everyone is done with the previous item
+            if (tid == 0) s_item = atomicAdd(p.sched, 1u);
             __syncthreads();
+            item = s_item;
         }
-    }
+        if (item >= total) break;
+        const unsigned chunk = item / p.chains, chain = item - chunk * p.chains;
+        const size_t ct0 = (size_t)chain * Cfg::CT;
+        // ciphertext slots beyond the batch replay the last ciphertext and store nothing
+        auto ct_of = [&](int slot) { size_t c = ct0 + slot; return c < p.batch ? c : p.batch - 1; };
+        const int step0 = (int)chunk * p.steps_per_chunk;
+        const int step1 = p.plain ? 1 : min(p.n, step0 + p.steps_per_chunk);
 
-    for (int e = tid; e < Cfg::CT * 2 * NTT_N; e += Cfg::THREADS) {
-        const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);
-        const size_t c = ct0 + slot;
-        if (c >= p.batch) continue;
-        if (p.accum_out) p.accum_out[(c * 2 + mi) * NTT_N + x] = s.acc[e];
-        if (p.extract) {
-            // sample extraction (tlwe_gpu.mako:63-82; blind_rotate.mako:213-224)
-            const i32 *a0 = s.acc + slot * 2 * NTT_N;
-            if (mi == 0) p.out_a[c * NTT_N + x] = x == 0 ? a0[0] : (i32)(0u - (u32)a0[NTT_N - x]);
-            else if (x == 0) p.out_b[c] = a0[NTT_N];
+        if (chunk == 0) {
+            // accumulator initialisation: CT x 2 polynomials x 1024 coefficients
+            for (int e = tid; e < ACC_WORDS; e += Cfg::THREADS) {
+                const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);
+                const size_t c = ct_of(slot);
+                i32 val;
+                if (p.accum) {
+                    val = p.accum[(c * 2 + mi) * NTT_N + x];
+                } else {
+                    // ACC = (0, X^(2N - barb) * [mu, ..., mu])   (bootstrap.py:177-182, 224)
+                    u32 xb;
+                    if (p.job_batch && c >= p.job_batch) {
+                        const size_t d = c - p.job_batch;
+                        xb = (u32)p.j2_c + (u32)p.j2_s1 * (u32)p.j2_in1_b[d] + (p.j2_in2_b ? (u32)p.j2_s2 * (u32)p.j2_in2_b[d] : 0u);
+                    } else {
+                        xb = (u32)p.c + (u32)p.s1 * (u32)p.in1_b[c] + (p.in2_b ? (u32)p.s2 * (u32)p.in2_b[c] : 0u);
+                    }
+                    int q = 2 * NTT_N - modswitch_2n((i32)xb);
+                    if (q < NTT_N) val = x < q ? (i32)(0u - (u32)p.mu) : p.mu;
+                    else val = x < q - NTT_N ? p.mu : (i32)(0u - (u32)p.mu);
+                    if (mi == 0) val = 0;
+                }
+                s.acc[e] = val;
+            }
+        } else {
+            // resume a parked chain: wait until its previous chunk has been published, then fetch the accumulators
+            if (tid == 0) {
+                while (ld_acquire_u32(p.sched + BR_SCHED_HEADER + chain) < chunk) __nanosleep(200);
+            }
+            __syncthreads();
+            const int4 *src = reinterpret_cast<const int4 *>(p.state + (size_t)chain * ACC_WORDS);
+            for (int e = tid; e < ACC_WORDS / 4; e += Cfg::THREADS) reinterpret_cast<int4 *>(s.acc)[e] = __ldcg(src + e);
         }
+
+        if (p.plain) {
+            __syncthreads();
+            br2_step<false, Cfg>(s, p.bk, s.rot, tid);
+            __syncthreads();
+        } else {
+            if (tid < Cfg::CT) s.rot[(step0 & 1) * Cfg::CT + tid] = br2_rotation(p, ct_of(tid), step0);
+            __syncthreads();
+            for (int i = step0; i < step1; i++) {
+                int next = 0;
+                if (tid < Cfg::CT && i + 1 < step1) next = br2_rotation(p, ct_of(tid), i + 1);
+                br2_step<true, Cfg>(s, p.bk + (size_t)i * BK_ROW_U64, s.rot + (i & 1) * Cfg::CT, tid);
+                if (tid < Cfg::CT) s.rot[((i + 1) & 1) * Cfg::CT + tid] = next;
+                __syncthreads();
+            }
+        }
+
+        if (!p.plain && step1 < p.n) {
+            // park the accumulators and publish the chain's progress
+            int4 *dst = reinterpret_cast<int4 *>(p.state + (size_t)chain * ACC_WORDS);
+            for (int e = tid; e < ACC_WORDS / 4; e += Cfg::THREADS) __stcg(dst + e, reinterpret_cast<const int4 *>(s.acc)[e]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release_u32(p.sched + BR_SCHED_HEADER + chain, chunk + 1);
+        } else {
+            for (int e = tid; e < ACC_WORDS; e += Cfg::THREADS) {
+                const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);
+                const size_t c = ct0 + slot;
+                if (c >= p.batch) continue;
+                if (p.accum_out) p.accum_out[(c * 2 + mi) * NTT_N + x] = s.acc[e];
+                if (p.extract) {
+                    // sample extraction (tlwe_gpu.mako:63-82; blind_rotate.mako:213-224)
+                    const i32 *a0 = s.acc + slot * 2 * NTT_N;
+                    if (mi == 0) p.out_a[c * NTT_N + x] = x == 0 ? a0[0] : (i32)(0u - (u32)a0[NTT_N - x]);
+                    else if (x == 0) p.out_b[c] = a0[NTT_N];
+                }
+            }
+        }
+        if (!p.sched) break;
     }
 }
 
@@ -476,6 +602,13 @@ constexpr int KS_CONSUMERS = 256;           // threads 0..249: a[2t], a[2t+1] of
 constexpr int KS_THREADS = KS_CONSUMERS + 64;   // + producer warp (TMA issue) + b/variance warp
 constexpr int KS_SLOTS = 4;                 // ring of half-j slots (4 values of k each): two j in flight
 constexpr int KS_IN = 1024, KS_N = 500;     // fast-path sizes (api_low_level.py:49-50)
+// The variance of a result is a float32 sum of 8192 table entries.  Float addition is not associative, so its shape is
+// FIXED: 128 block sums over 8 consecutive input coefficients each (64 terms, added in (j, k) order), then the block
+// sums added in block order.  A CTA that owns only a slice of j (small batches, KeyswitchArgs::splits) writes its
+// block sums to a scratch array and ks_cv_finalize_kernel adds them; a CTA that owns all of j does both itself.
+// Either way the same additions happen in the same order: bit-identical variances for every launch shape, run to run.
+constexpr int KS_CV_BLOCK_J = 8;
+constexpr int KS_CV_BLOCKS = KS_IN / KS_CV_BLOCK_J;
 constexpr int KS_ROW_BYTES = KS_N * 4;
 constexpr int KS_SLOT_BYTES = 4 * 4 * KS_ROW_BYTES;   // 4 k x 4 rows
 constexpr size_t KS_SMEM_BYTES = (size_t)KS_SLOTS * KS_SLOT_BYTES + (size_t)KS_IN * KS_TILE * 2 + 2 * KS_SLOTS * 8 + 128;
@@ -491,10 +624,10 @@ struct KeyswitchArgs {
     int tile;                                        // ciphertexts per CTA (fast path)
     int splits;                                      // > 1: blockIdx.y takes a slice of j and results are
                                                      // accumulated with integer atomics into zeroed outputs
+    float *cv_blocks;                                // splits > 1 and res_cv: (B, KS_CV_BLOCKS) partial variances
     size_t batch;
 };
 
-NB_D u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 NB_D void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
 NB_D void mbar_expect_tx(u64 *bar, u32 bytes)
 {
@@ -531,7 +664,7 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
     const int nct = (int)min((size_t)p.tile, p.batch - ct0);
     // slice of the input coefficients handled by this CTA (small batches: split-j over blockIdx.y so that
     // one ciphertext does not stream the whole 65 MB key through a single SM); always an even number of j
-    const int j_per = ((KS_IN + p.splits - 1) / p.splits + 1) & ~1;
+    const int j_per = ((KS_IN + p.splits - 1) / p.splits + KS_CV_BLOCK_J - 1) & ~(KS_CV_BLOCK_J - 1);
     const int j_begin = blockIdx.y * j_per;
     const int j_end = min(KS_IN, j_begin + j_per);
     const bool split = p.splits > 1;
@@ -565,31 +698,19 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
         float4 kc = __ldg(reinterpret_cast<const float4 *>(p.ks_cv));
         kb = __ldg(reinterpret_cast<const int4 *>(p.ks_b) + min(j_begin * 8, KS_IN * 8 - 1));
         kc = __ldg(reinterpret_cast<const float4 *>(p.ks_cv) + min(j_begin * 8, KS_IN * 8 - 1));
+        float blk = 0.f;
         for (int jk = j_begin * 8; jk < j_end * 8; jk++) {
             const int4 kb_next = __ldg(reinterpret_cast<const int4 *>(p.ks_b) + min(jk + 1, KS_IN * 8 - 1));
             const float4 kc_next = __ldg(reinterpret_cast<const float4 *>(p.ks_cv) + min(jk + 1, KS_IN * 8 - 1));
             const u32 bits = digits[(jk >> 3) * KS_TILE + q];
             const u32 d = (bits >> (14 - 2 * (jk & 7))) & 3u;
             accb -= d == 0 ? (u32)kb.x : d == 1 ? (u32)kb.y : d == 2 ? (u32)kb.z : (u32)kb.w;
-            cv += d == 0 ? kc.x : d == 1 ? kc.y : d == 2 ? kc.z : kc.w;
+            blk += d == 0 ? kc.x : d == 1 ? kc.y : d == 2 ? kc.z : kc.w;
             kb = kb_next; kc = kc_next;
-        }
-        if (split && blockIdx.y == 0 && p.res_cv) {
-            // The variance is a float32 running sum in (j, k) order (lwe_cpu.py:90-93); float addition is not
-            // associative, so with split j-ranges the y = 0 CTA alone walks all 1024 coefficients (from global
-            // memory: its shared-memory digits cover its own slice only).  Same order as the unsplit path.
-            cv = 0.f;
-            const size_t row = (ct0 + min(q, nct - 1)) * KS_IN;
-            for (int j = 0; j < KS_IN; j++) {
-                u32 v = (u32)__ldg(p.src1_a + row + j);
-                if (p.src2_a) v += (u32)__ldg(p.src2_a + row + j);
-                const u32 bits = (v + prec_offset) >> 16;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const float4 kc4 = __ldg(reinterpret_cast<const float4 *>(p.ks_cv) + j * 8 + k);
-                    const u32 d = (bits >> (14 - 2 * k)) & 3u;
-                    cv += d == 0 ? kc4.x : d == 1 ? kc4.y : d == 2 ? kc4.z : kc4.w;
-                }
+            if ((jk & (8 * KS_CV_BLOCK_J - 1)) == 8 * KS_CV_BLOCK_J - 1) {      // end of a block of 8 coefficients
+                if (split) { if (p.cv_blocks && q < nct) p.cv_blocks[(ct0 + q) * KS_CV_BLOCKS + (jk >> 6)] = blk; }
+                else cv += blk;
+                blk = 0.f;
             }
         }
         if (q < nct) {
@@ -599,7 +720,6 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
                 if (p.res_cv) p.res_cv[ct0 + q] = cv;
             } else {
                 atomicAdd(reinterpret_cast<unsigned int *>(p.res_b + ct0 + q), (blockIdx.y == 0 ? b : 0u) + accb);
-                if (p.res_cv && blockIdx.y == 0) p.res_cv[ct0 + q] = cv;
             }
         }
         return;
@@ -682,6 +802,21 @@ __global__ void __launch_bounds__(KS_THREADS, 1) keyswitch_kernel(KeyswitchArgs 
     }
 }
 
+// second half of the fixed-shape variance sum for split launches: one thread per ciphertext adds its block sums in order
+__global__ void ks_cv_finalize_kernel(float *__restrict__ res_cv, const float *__restrict__ cv_blocks, size_t batch)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= batch) return;
+    const float4 *src = reinterpret_cast<const float4 *>(cv_blocks + c * KS_CV_BLOCKS);
+    float cv = 0.f;
+#pragma unroll 8
+    for (int m = 0; m < KS_CV_BLOCKS / 4; m++) {
+        const float4 v = src[m];
+        cv += v.x; cv += v.y; cv += v.z; cv += v.w;
+    }
+    res_cv[c] = cv;
+}
+
 // Generic decomposition parameters (API parity with LweKeyswitch(…, decomp_length, log2_base)): the
 // straightforward per-ciphertext gather.
 __global__ void __launch_bounds__(512) keyswitch_generic_kernel(KeyswitchArgs p)
@@ -728,6 +863,82 @@ __global__ void lwe_affine_kernel(i32 *res_a, i32 *res_b, const i32 *x1_a, const
             u32 v = (u32)c + (x1_b ? (u32)s1 * (u32)x1_b[b] : 0u);
             if (x2_b) v += (u32)s2 * (u32)x2_b[b];
             res_b[b] = (i32)v;
+        }
+    }
+}
+
+// ---- LWE encryption / phase (lwe_gpu.py:186-284, lwe_gpu.mako:205-262; lwe_cpu.py:96-113) and the key-switch key
+// (lwe_gpu.py:63-124, lwe_gpu.mako:18-56; lwe_cpu.py:26-59): wrap-around dot products with the binary key.  One warp
+// per row, 16-byte loads when the row length allows; nothing is materialised in 64 bits.
+
+// out[i] = add1[i] (+ add2[i]) + sign * <a[i, :], key>   (Torus32, mod 2^32)
+//   encrypt: add1 = messages, add2 = Gaussian noise, sign = +1, a = the uniform mask      (b = mu + e + <a, s>)
+//   phase:   add1 = b, sign = -1                                                          (b - <a, s>)
+__global__ void lwe_dot_kernel(i32 *__restrict__ out, const i32 *__restrict__ a, const i32 *__restrict__ key,
+                               const i32 *__restrict__ add1, const i32 *__restrict__ add2, i32 sign, size_t batch, int n)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < batch; row += warps) {
+        const i32 *ar = a + row * (size_t)n;
+        u32 acc = 0;
+        if ((n & 3) == 0) {
+            const int4 *a4 = reinterpret_cast<const int4 *>(ar);
+            const int4 *k4 = reinterpret_cast<const int4 *>(key);
+            for (int j = lane; j < n / 4; j += 32) {
+                const int4 x = __ldg(a4 + j), k = __ldg(k4 + j);
+                acc += (u32)x.x * (u32)k.x + (u32)x.y * (u32)k.y + (u32)x.z * (u32)k.z + (u32)x.w * (u32)k.w;
+            }
+        } else {
+            for (int j = lane; j < n; j += 32) acc += (u32)__ldg(ar + j) * (u32)__ldg(key + j);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            u32 v = (u32)sign * acc;
+            if (add1) v += (u32)add1[row];
+            if (add2) v += (u32)add2[row];
+            out[row] = (i32)v;
+        }
+    }
+}
+
+// key-switch key: row (i, j, h) of ks_a / ks_b / ks_cv; h = 0 is the zero padding, h >= 1 encrypts
+// in_key[i] * h * 2^(32 - (j + 1) log2_base) under out_key with mask noises_a[i, j, h - 1] and noise noises_b[i, j, h - 1]
+__global__ void make_keyswitch_key_kernel(i32 *__restrict__ ks_a, i32 *__restrict__ ks_b, float *__restrict__ ks_cv,
+                                          const i32 *__restrict__ in_key, const i32 *__restrict__ out_key,
+                                          const i32 *__restrict__ noises_a, const i32 *__restrict__ noises_b,
+                                          size_t in_size, int n, int t, int log2_base, float noise_var)
+{
+    const int base = 1 << log2_base;
+    const size_t rows = in_size * t * base;
+    const int lane = threadIdx.x & 31;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+        const int h = (int)(row % base);
+        const size_t ij = row / base;
+        const int j = (int)(ij % t);
+        const size_t i = ij / t;
+        i32 *dst = ks_a + row * (size_t)n;
+        if (h == 0) {
+            for (int x = lane; x < n; x += 32) dst[x] = 0;
+            if (lane == 0) { ks_b[row] = 0; ks_cv[row] = 0.f; }
+            continue;
+        }
+        const size_t nrow = ij * (base - 1) + (h - 1);
+        const i32 *src = noises_a + nrow * (size_t)n;
+        u32 acc = 0;
+        for (int x = lane; x < n; x += 32) {
+            const i32 v = __ldg(src + x);
+            dst[x] = v;
+            acc += (u32)v * (u32)__ldg(out_key + x);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            const u32 message = (u32)in_key[i] * (u32)h * (1u << (32 - (j + 1) * log2_base));
+            ks_b[row] = (i32)(message + (u32)noises_b[nrow] + acc);
+            ks_cv[row] = noise_var;
         }
     }
 }

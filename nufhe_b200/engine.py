@@ -258,6 +258,29 @@ class Engine:
         self._call('nb_t32_to_phase', _ptr(out), _ptr(messages), out.numel(), int(mspace_size))
         return out
 
+    def lwe_dot(self, a, key, add1=None, add2=None, sign=1, out=None):
+        """out[i] = add1[i] + add2[i] + sign * <a[i], key> in Torus32 (nb_lwe_dot); a (..., n), key (n,)."""
+        a = self._dense(a, torch.int32)
+        key = self._dense(key, torch.int32)
+        n = key.numel()
+        shape = tuple(a.shape[:-1])
+        if out is None:
+            out = self.empty(shape, torch.int32)
+        assert out.is_contiguous() and out.dtype == torch.int32
+        add1 = self._dense(add1, torch.int32) if add1 is not None else None
+        add2 = self._dense(add2, torch.int32) if add2 is not None else None
+        self._call('nb_lwe_dot', _ptr(out), _ptr(a), _ptr(key), _ptr(add1), _ptr(add2), int(sign), a.numel() // n, n)
+        return out
+
+    def make_keyswitch_key(self, ks_a, ks_b, ks_cv, in_key, out_key, noises_a, noises_b, log2_base, noise_variance):
+        """Fill a key-switch key (nb_make_keyswitch_key); ks_a (in, t, base, n) etc. dense, updated in place."""
+        assert ks_a.is_contiguous() and ks_b.is_contiguous() and ks_cv.is_contiguous()
+        in_size, t, base, n = ks_a.shape
+        self._call('nb_make_keyswitch_key', _ptr(ks_a), _ptr(ks_b), _ptr(ks_cv), _ptr(self._dense(in_key, torch.int32)),
+                   _ptr(self._dense(out_key, torch.int32)), _ptr(self._dense(noises_a, torch.int32)),
+                   _ptr(self._dense(noises_b, torch.int32)), in_size, n, t, int(log2_base),
+                   ctypes.c_float(float(noise_variance)))
+
     def lwe_affine(self, res, x1, x2, c, s1, s2):
         res_a, res_b = res
         B = res_b.numel()

@@ -9,7 +9,7 @@ import pickle
 import numpy
 import torch
 
-from .utils import arrays_equal, wrapping_dot
+from .utils import arrays_equal
 from .numeric_functions import Torus32, ErrorFloat
 from .random_numbers import rand_uniform_bool, rand_uniform_torus32, rand_gaussian_torus32
 
@@ -195,7 +195,7 @@ class LweKeyswitchKey:
             thr, rng, 0, noise, (input_size, ks_decomp_length, base - 1), centered=True)
         noises_a = rand_uniform_torus32(
             thr, rng, (input_size, ks_decomp_length, base - 1, output_size))
-        make_lwe_keyswitch_key(lwe, in_key.key, out_key.key, noises_a, noises_b, ks_log2_base, noise)
+        make_lwe_keyswitch_key(thr, lwe, in_key.key, out_key.key, noises_a, noises_b, ks_log2_base, noise)
         return cls(lwe)
 
     def dump(self, file_obj):
@@ -213,24 +213,12 @@ class LweKeyswitchKey:
         return (lwe.a.contiguous(), lwe.b.contiguous(), lwe.current_variances.contiguous())
 
 
-def make_lwe_keyswitch_key(lwe, in_key, out_key, noises_a, noises_b, log2_base, noise):
+def make_lwe_keyswitch_key(thr, lwe, in_key, out_key, noises_a, noises_b, log2_base, noise):
     """MakeLweKeyswitchKey (lwe_gpu.py:63-124, lwe_gpu.mako:18-56; ref lwe_cpu.py:26-59): row h=0 is
-    zero padding, row h encrypts in_key[i] * h * 2^(32 - (j+1) log2_base) under out_key."""
-    input_size, t, base = lwe.shape
-    dev = lwe.a.device
-    hs = torch.arange(1, base, device=dev, dtype=torch.int64)
-    js = torch.arange(t, device=dev, dtype=torch.int64)
-    messages = (in_key.to(torch.int64)[:, None, None] * hs[None, None, :]
-                * (2 ** (32 - (js[None, :, None] + 1) * log2_base)))
-    total = messages + noises_b.to(torch.int64) + wrapping_dot(noises_a, out_key).to(torch.int64)
-    total = total & 0xffffffff
-    total = torch.where(total >= 2**31, total - 2**32, total).to(torch.int32)
-    lwe.a[:, :, 0, :] = 0
-    lwe.b[:, :, 0] = 0
-    lwe.current_variances[:, :, 0] = 0
-    lwe.a[:, :, 1:, :] = noises_a
-    lwe.b[:, :, 1:] = total
-    lwe.current_variances[:, :, 1:] = float(numpy.float32(noise**2))
+    zero padding, row h encrypts in_key[i] * h * 2^(32 - (j+1) log2_base) under out_key.  One engine kernel
+    (nb_make_keyswitch_key); the result arrays of a fresh LweSampleArray are dense."""
+    thr.make_keyswitch_key(lwe.a, lwe.b, lwe.current_variances, in_key, out_key, noises_a, noises_b, log2_base,
+                           numpy.float32(noise**2))
 
 
 def _dense_pair(thr, sample: LweSampleArray):
@@ -255,23 +243,21 @@ def _keyswitch_into(thr, result, ks, sample1, sample2, const):
 
 
 def lwe_encrypt(thr, rng, result: LweSampleArray, messages, noise: float, key: LweKey):
-    """lwe.py:325-333; b = noise + mu + <a, s> (lwe_gpu.py:217-241)"""
+    """lwe.py:325-333; b = noise + mu + <a, s> (lwe_gpu.py:217-241) -- nb_lwe_dot, no 64-bit temporaries"""
     lwe_size = key.params.size
     noises_b = rand_gaussian_torus32(thr, rng, 0, noise, tuple(messages.shape))
     noises_a = rand_uniform_torus32(thr, rng, tuple(messages.shape) + (lwe_size,))
     result.a.copy_(noises_a)
-    total = noises_b.to(torch.int64) + messages.to(torch.int64) + wrapping_dot(noises_a, key.key).to(torch.int64)
-    total = total & 0xffffffff
-    result.b.copy_(torch.where(total >= 2**31, total - 2**32, total).to(torch.int32))
+    b = thr.lwe_dot(noises_a, key.key, add1=messages.to(torch.int32), add2=noises_b, sign=1,
+                    out=result.b if result.b.is_contiguous() else None)
+    if b is not result.b:
+        result.b.copy_(b)
     result.current_variances.fill_(float(numpy.float32(noise**2)))
 
 
 def lwe_decrypt(thr, sample: LweSampleArray, key: LweKey):
-    """lwe.py:336-343; phase = b - <a, s> (lwe_gpu.py:246-284).  Returns a host array."""
-    d = sample.b.to(torch.int64) - wrapping_dot(sample.a, key.key).to(torch.int64)
-    d = d & 0xffffffff
-    d = torch.where(d >= 2**31, d - 2**32, d).to(torch.int32)
-    return d.cpu().numpy()
+    """lwe.py:336-343; phase = b - <a, s> (lwe_gpu.py:246-284) -- nb_lwe_dot.  Returns a host array."""
+    return thr.lwe_dot(sample.a, key.key, add1=sample.b, sign=-1).cpu().numpy()
 
 
 def _broadcast_source(result_part, source_part, trailing):

@@ -148,6 +148,34 @@ class FakeEngine:
             ra, rb = out
         return ra, rb, (rcv if want_cv else None)
 
+    def lwe_dot(self, a, key, add1=None, add2=None, sign=1, out=None):
+        """nb_lwe_dot restated with NumPy (vec_mul_mat of nufhe/lwe_cpu.py:22-23 + the addends)."""
+        an, kn = _np(a).astype(numpy.int64), _np(key).astype(numpy.int64)
+        v = int(sign) * (an * kn).sum(-1)
+        for add in (add1, add2):
+            if add is not None:
+                v = v + _np(add).astype(numpy.int64).reshape(v.shape)
+        res = _t(_wrap32(v)).reshape(tuple(a.shape[:-1]))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def make_keyswitch_key(self, ks_a, ks_b, ks_cv, in_key, out_key, noises_a, noises_b, log2_base, noise_variance):
+        """nb_make_keyswitch_key restated with NumPy (MakeLweKeyswitchKeyReference, nufhe/lwe_cpu.py:26-59)."""
+        in_size, t, base, n = ks_a.shape
+        na, nb_ = _np(noises_a).astype(numpy.int64), _np(noises_b).astype(numpy.int64)
+        hs = numpy.arange(1, base, dtype=numpy.int64)[None, None, :]
+        js = numpy.arange(t, dtype=numpy.int64)[None, :, None]
+        messages = _np(in_key).astype(numpy.int64)[:, None, None] * hs * (2 ** (32 - (js + 1) * log2_base))
+        b = messages + nb_ + (na * _np(out_key).astype(numpy.int64)).sum(-1)
+        ks_a[:, :, 0, :] = 0
+        ks_a[:, :, 1:, :] = noises_a
+        ks_b[:, :, 0] = 0
+        ks_b[:, :, 1:] = _t(_wrap32(b))
+        ks_cv[:, :, 0] = 0
+        ks_cv[:, :, 1:] = float(noise_variance)
+
     def lwe_affine(self, res, x1, x2, c, s1, s2):
         zero = (torch.zeros_like(res[0]), torch.zeros_like(res[1]))
         a, b = self._affine(x1 if x1 is not None else zero, x2, c, s1 if x1 is not None else 0, s2)

@@ -140,3 +140,128 @@ def test_both_cta_shapes_give_the_same_bits(keys, monkeypatch):
             assert (keys.decrypt(out) == ~(bits_a & bits_b)).all()
         for x, y in zip(outs[(B, '0')], outs[(B, '1000000')]):
             assert (x[0] == y[0]).all() and (x[1] == y[1]).all(), B
+
+
+# ---- BASELINE.md section 4 parity set --------------------------------------------------------------------------
+
+def test_nand32_and_mux_match_reference_closures(eng, keys, dev_keys, golden):
+    """32 NAND ciphertexts and 4 MUX triples against tests/golden/gates32.npz -- inputs, extracted samples and final
+    ciphertexts produced by the UNMODIFIED reference's NumPy closures (make_golden_gates32.py), same keys as
+    gate.npz.  Bit-exact on every (a, b)."""
+    g = golden('gates32')
+    bk_int, ks = dev_keys
+    ext, out = gpu_gate(eng, dev_keys, 'nand', (g['in1_a'], g['in1_b']), (g['in2_a'], g['in2_b']))
+    assert (ext[0] == g['nand_ext_a']).all() and (ext[1] == g['nand_ext_b']).all()
+    assert (out[0] == g['nand_a']).all() and (out[1] == g['nand_b']).all()
+    assert (keys.decrypt(out) == ~(g['bits_a'] & g['bits_b'])).all()
+    d = [(eng.to_device(g['mux_in_a'][i]), eng.to_device(g['mux_in_b'][i])) for i in range(3)]
+    and_const = O.phase_to_t32(-1, 8)
+    u1, u2 = eng.bootstrap_extract2((d[0], d[1], and_const, 1, 1), (d[0], d[2], and_const, -1, 1), O.MU, bk_int)
+    assert (eng.to_host(u1[0]) == g['mux_u1_a']).all() and (eng.to_host(u1[1]) == g['mux_u1_b']).all()
+    assert (eng.to_host(u2[0]) == g['mux_u2_a']).all() and (eng.to_host(u2[1]) == g['mux_u2_b']).all()
+    ma, mb, _ = eng.keyswitch(ks, u1, u2, c=O.phase_to_t32(1, 8))
+    assert (eng.to_host(ma) == g['mux_a']).all() and (eng.to_host(mb) == g['mux_b']).all()
+    mb_ = g['mux_bits']
+    assert (keys.decrypt((eng.to_host(ma), eng.to_host(mb))) == numpy.where(mb_[0], mb_[1], mb_[2])).all()
+
+
+def test_vm_gate_mux_matches_reference_closures(golden):
+    """The same MUX through the public API (Context -> VirtualMachine.gate_mux, nufhe/gates.py:600-664)."""
+    import nufhe_b200 as nufhe
+    from nufhe_b200.lwe import LweSampleArray
+    g = golden('gates32')
+    ctx = nufhe.Context(rng=nufhe.DeterministicRNG(G.GATE_SEED))
+    sk, ck = ctx.make_key_pair()
+    vm = ctx.make_virtual_machine(ck)
+    thr = ctx.thread
+    cts = [LweSampleArray(ck.params.in_out_params, thr.to_device(g['mux_in_a'][i]), thr.to_device(g['mux_in_b'][i]),
+                          torch.zeros(4, dtype=torch.float32, device=thr.device)) for i in range(3)]
+    r = vm.gate_mux(*cts)
+    assert (r.a.cpu().numpy() == g['mux_a']).all() and (r.b.cpu().numpy() == g['mux_b']).all()
+
+
+def test_full_4096_nand_and_mux_equal_the_oracle(eng, keys, dev_keys):
+    """bit-exact against the CPU oracle on ALL 4096 outputs, NAND and MUX (the oracle runs
+    ~70 s + ~140 s on 16 host cores).  4096 x 500 steps x 8192 multiplications put a few elements on the rare path
+    of the deferred canonicalisation (probability 2^-32 each), so this is also its end-to-end check."""
+    bk_int, ks = dev_keys
+    B = 4096
+    rng = G.rs(4096)
+    bits = [rng.randint(0, 2, B).astype(bool) for _ in range(3)]
+    a, b, c = (keys.encrypt(x) for x in bits)
+    ext, out = gpu_gate(eng, dev_keys, 'nand', a, b)
+    want = O.gate_binary('nand', a, b, keys.bk, keys.ks)
+    assert (out[0] == want[0]).all() and (out[1] == want[1]).all()
+    d = [(eng.to_device(x[0]), eng.to_device(x[1])) for x in (a, b, c)]
+    and_const = O.phase_to_t32(-1, 8)
+    u1, u2 = eng.bootstrap_extract2((d[0], d[1], and_const, 1, 1), (d[0], d[2], and_const, -1, 1), O.MU, bk_int)
+    ma, mb, _ = eng.keyswitch(ks, u1, u2, c=O.phase_to_t32(1, 8))
+    want = O.gate_mux(a, b, c, keys.bk, keys.ks)
+    assert (eng.to_host(ma) == want[0]).all() and (eng.to_host(mb) == want[1]).all()
+    assert (keys.decrypt(want) == numpy.where(bits[0], bits[1], bits[2])).all()
+
+
+def test_batch_65536_truth_table_and_strided_oracle_subset(eng, keys, dev_keys):
+    """BASELINE.json config 5's batch on one GPU: every output decrypts to NAND, and a strided 512-ciphertext subset
+    equals the oracle bit for bit."""
+    B = 65536
+    rng = G.rs(65536)
+    bits_a, bits_b = rng.randint(0, 2, B).astype(bool), rng.randint(0, 2, B).astype(bool)
+    a, b = keys.encrypt(bits_a), keys.encrypt(bits_b)
+    ext, out = gpu_gate(eng, dev_keys, 'nand', a, b)
+    assert (keys.decrypt(out) == ~(bits_a & bits_b)).all()
+    sub = slice(17, None, 128)
+    want = O.gate_binary('nand', (a[0][sub], a[1][sub]), (b[0][sub], b[1][sub]), keys.bk, keys.ks)
+    assert (out[0][sub] == want[0]).all() and (out[1][sub] == want[1]).all()
+
+
+@pytest.mark.parametrize('batch', [700, 1030])
+def test_time_sliced_launches_equal_the_oracle(eng, keys, dev_keys, batch):
+    """Batches between one and two waves are cut into chunks of steps that migrate between CTAs (accumulators parked
+    in global memory, kernels.cuh: blind_rotate_kernel); every ciphertext must still equal the oracle."""
+    rng = G.rs(batch)
+    bits_a, bits_b = rng.randint(0, 2, batch).astype(bool), rng.randint(0, 2, batch).astype(bool)
+    a, b = keys.encrypt(bits_a), keys.encrypt(bits_b)
+    ext, out = gpu_gate(eng, dev_keys, 'nand', a, b)
+    want = O.gate_binary('nand', a, b, keys.bk, keys.ks)
+    assert (out[0] == want[0]).all() and (out[1] == want[1]).all()
+
+
+_RARE_PATH_SCRIPT = r'''
+import sys, numpy
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/tests/golden')
+import gen_inputs as G
+from oracle import oracle as O
+from nufhe_b200.engine import Engine
+eng = Engine()
+keys = O.OracleKeys(G.GATE_SEED)
+bk_int = eng.bk_prepare(eng.to_device(keys.bk))
+ks = (eng.to_device(keys.ks_a), eng.to_device(keys.ks_b), eng.to_device(keys.ks_cv))
+rng = G.rs(77)
+B = 9
+a, b = keys.encrypt(rng.randint(0, 2, B).astype(bool)), keys.encrypt(rng.randint(0, 2, B).astype(bool))
+ext = eng.bootstrap_extract((eng.to_device(a[0]), eng.to_device(a[1])), (eng.to_device(b[0]), eng.to_device(b[1])),
+                            O.phase_to_t32(1, 8), -1, -1, O.MU, bk_int)
+ra, rb, _ = eng.keyswitch(ks, ext)
+want = O.gate_binary('nand', a, b, keys.bk, keys.ks)
+assert (eng.to_host(ra) == want[0]).all() and (eng.to_host(rb) == want[1]).all()
+x = numpy.random.RandomState(5).randint(-2**31, 2**31, (64, 1024)).astype(numpy.int32)
+f = eng.ntt_forward_i32(eng.to_device(x))
+assert (eng.to_host(eng.ntt_inverse_i32(f)) == x).all()
+print('rare path ok')
+'''
+
+
+@pytest.mark.parametrize('wide_max', ['0', '1000000'])
+def test_canonicalisation_rare_path_forced(wide_max):
+    """NUFHE_B200_FORCE_RARE_PATH=1 lowers the trigger of the deferred canonicalisation so that EVERY task of fwd1,
+    inv1 and the MAC runs its fix-up code (normally 2^-32 per element); results must not change.  Runs in a fresh
+    process because the trigger is a __constant__ set when the context is created."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NUFHE_B200_FORCE_RARE_PATH='1', NUFHE_B200_WIDE_MAX=wide_max)
+    r = subprocess.run([sys.executable, '-c', _RARE_PATH_SCRIPT % {'root': root}], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and 'rare path ok' in r.stdout, r.stdout + r.stderr

@@ -304,3 +304,89 @@ def test_external_product_steps_vs_oracle(eng, k, batch):
     mac = eng.tgsw_mac(tr, dev_u64(eng, bk_row), k, 2)
     assert (eng.to_host(mac, True) == O.tgsw_mac_k(eng.to_host(tr, True), bk_row)).all()
     assert (eng.to_host(eng.ntt_inverse_i32(mac)) == O.tgsw_external_mul_k(accum, bk_row)).all()
+
+
+def test_keyswitch_variances_are_reproducible_across_launch_shapes(eng):
+    """The variance is a float32 sum of fixed shape (block sums of 8 coefficients, then the blocks in order), whatever
+    the launch: batches small enough to split the input coefficients over many CTAs (1 ciphertext: 128 slices) give
+    the same bits as a big batch that does not split, run after run; and it agrees with the oracle's plain running
+    sum to float accuracy (the reference's own test uses allclose, test_lwe.py:101)."""
+    rng = G.rs(15)
+    ks_a, ks_b, _, _, _ = G.keyswitch_inputs()
+    ks_cv = (rng.uniform(0.0, 1e-6, size=ks_b.shape) * (numpy.arange(4) > 0)).astype(numpy.float32)   # row d = 0 is padding
+    ks = (eng.to_device(ks_a), eng.to_device(ks_b), eng.to_device(ks_cv))
+    B = 4800                                                       # 150 tiles >= 148 SMs: no split
+    src_a, src_b = G.torus32(rng, (B, 1024)), G.torus32(rng, (B,))
+    da, db = eng.to_device(src_a), eng.to_device(src_b)
+    _, _, cv_big = eng.keyswitch(ks, (da, db), want_cv=True)
+    cv_big = eng.to_host(cv_big)
+    _, _, want = O.lwe_keyswitch(ks_a, ks_b, ks_cv, src_a[:70], src_b[:70])
+    assert numpy.allclose(cv_big[:70], want, rtol=1e-5)
+    for b in (1, 5, 33, 70):
+        for _ in range(2):
+            ra, rb, cv = eng.keyswitch(ks, (da[:b].contiguous(), db[:b].contiguous()), want_cv=True)
+            assert (eng.to_host(cv) == cv_big[:b]).all(), b
+
+
+def test_tlwe_noiseless_trivial_writes_one_variance_per_sample(eng):
+    """Regression: the kernel used to zero B * (k + 1) floats of a (B,) variance array.  A canary right behind the
+    variances (same allocation) must survive, for k = 1 and k = 2 and batches beyond the allocator's rounding."""
+    for k, B in ((1, 300), (2, 129)):
+        buf = torch.full((2 * B + 64,), 7.0, dtype=torch.float32, device=eng.device)
+        cv = buf[:B]
+        acc = eng.empty((B, k + 1, 1024), torch.int32)
+        mu = torch.arange(B * 1024, dtype=torch.int32, device=eng.device).reshape(B, 1024)
+        eng.tlwe_noiseless_trivial(acc, cv, mu)
+        assert bool((buf[:B] == 0).all()) and bool((buf[B:] == 7.0).all())
+        assert bool((acc[:, k] == mu).all()) and bool((acc[:, :k] == 0).all())
+
+
+@pytest.mark.parametrize('n', [500, 501, 1024, 3])
+def test_lwe_dot(eng, n):
+    """nb_lwe_dot (LweEncrypt / LweDecrypt, lwe_gpu.mako:205-262): wrap-around dot product with the key plus addends,
+    16-byte path (n % 4 == 0) and scalar path, against exact integer arithmetic."""
+    rng = G.rs(600 + n)
+    for B in (1, 37, 2000):
+        a = G.torus32(rng, (B, n))
+        key = rng.randint(0, 2, size=(n,)).astype(numpy.int32)
+        add1, add2 = G.torus32(rng, (B,)), G.torus32(rng, (B,))
+        dot = (a.astype(numpy.int64) * key.astype(numpy.int64)).sum(-1)
+
+        def wrap(x):
+            return ((x + 2**31) % 2**32 - 2**31).astype(numpy.int32)
+        da, dk = eng.to_device(a), eng.to_device(key)
+        got = eng.to_host(eng.lwe_dot(da, dk, add1=eng.to_device(add1), add2=eng.to_device(add2), sign=1))
+        assert (got == wrap(dot + add1.astype(numpy.int64) + add2)).all()
+        got = eng.to_host(eng.lwe_dot(da, dk, add1=eng.to_device(add1), sign=-1))
+        assert (got == wrap(add1.astype(numpy.int64) - dot)).all()
+        assert (eng.to_host(eng.lwe_dot(da, dk)) == wrap(dot)).all()
+    # a general (non-binary) key wraps the same way
+    key = G.torus32(rng, (n,))
+    a = G.torus32(rng, (5, n))
+    want = numpy.array([sum(int(x) * int(k) for x, k in zip(row, key)) for row in a])
+    assert (eng.to_host(eng.lwe_dot(eng.to_device(a), eng.to_device(key))).astype(numpy.int64) == (want + 2**31) % 2**32 - 2**31).all()
+
+
+def test_make_keyswitch_key_small(eng):
+    """nb_make_keyswitch_key (lwe_gpu.mako:18-56) on a small shape against the formula of lwe_cpu.py:26-59; the full-size
+    key is pinned by the key digests of the reference (test_gpu_api.py::test_seeded_keys_equal_reference_keys)."""
+    rng = G.rs(77)
+    in_size, t, log2_base, n = 6, 3, 2, 10
+    base = 1 << log2_base
+    in_key = rng.randint(0, 2, size=(in_size,)).astype(numpy.int32)
+    out_key = rng.randint(0, 2, size=(n,)).astype(numpy.int32)
+    na, nb_ = G.torus32(rng, (in_size, t, base - 1, n)), G.torus32(rng, (in_size, t, base - 1))
+    ks_a = torch.full((in_size, t, base, n), 5, dtype=torch.int32, device=eng.device)
+    ks_b = torch.full((in_size, t, base), 5, dtype=torch.int32, device=eng.device)
+    ks_cv = torch.full((in_size, t, base), 5.0, dtype=torch.float32, device=eng.device)
+    eng.make_keyswitch_key(ks_a, ks_b, ks_cv, eng.to_device(in_key), eng.to_device(out_key), eng.to_device(na),
+                           eng.to_device(nb_), log2_base, 0.25)
+    a, b, cv = eng.to_host(ks_a), eng.to_host(ks_b), eng.to_host(ks_cv)
+    assert (a[:, :, 0] == 0).all() and (b[:, :, 0] == 0).all() and (cv[:, :, 0] == 0).all()
+    assert (a[:, :, 1:] == na).all() and (cv[:, :, 1:] == 0.25).all()
+    for i in range(in_size):
+        for j in range(t):
+            for h in range(1, base):
+                want = int(in_key[i]) * h * 2 ** (32 - (j + 1) * log2_base) + int(nb_[i, j, h - 1]) + int(
+                    (na[i, j, h - 1].astype(numpy.int64) * out_key).sum())
+                assert int(b[i, j, h]) == (want + 2**31) % 2**32 - 2**31

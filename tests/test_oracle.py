@@ -120,6 +120,33 @@ def test_gate_nand_matches_reference(golden, keys):
     assert (keys.decrypt(out) == g['nand_bits']).all()
 
 
+def test_nand32_and_mux_match_reference(golden, keys):
+    """BASELINE.md section 4's tier-0 set: 32 NAND ciphertexts and 4 MUX triples computed by the reference's own
+    closures (tests/golden/gates32.npz, make_golden_gates32.py) -- the oracle reproduces the inputs (same RNG draw
+    order after the three operands of gate.npz), the extracted samples and the final ciphertexts."""
+    g = golden('gates32')
+    assert sha(keys.lwe_key) == str(g['lwe_key_sha']) and sha(keys.bk) == str(g['bk_sha'])
+    fresh = O.OracleKeys(G.GATE_SEED)
+    for bits in (G.GATE_BITS_A, G.GATE_BITS_B, G.GATE_BITS_C):
+        fresh.encrypt(bits)
+    d1, d2 = fresh.encrypt(g['bits_a']), fresh.encrypt(g['bits_b'])
+    m = [fresh.encrypt(g['mux_bits'][i]) for i in range(3)]
+    assert (d1[0] == g['in1_a']).all() and (d1[1] == g['in1_b']).all() and (d2[0] == g['in2_a']).all()
+    for i in range(3):
+        assert (m[i][0] == g['mux_in_a'][i]).all() and (m[i][1] == g['mux_in_b'][i]).all()
+    num, den, sa, sb = O.GATE_TABLE['nand']
+    t = O.lwe_affine2(d1, d2, O.phase_to_t32(num, den), sa, sb)
+    ext = O.bootstrap(t[0], t[1], keys.bk, None)
+    assert (ext[0] == g['nand_ext_a']).all() and (ext[1] == g['nand_ext_b']).all()
+    out = O.gate_binary('nand', d1, d2, keys.bk, keys.ks)
+    assert (out[0] == g['nand_a']).all() and (out[1] == g['nand_b']).all()
+    t1 = O.lwe_affine2(m[0], m[1], O.phase_to_t32(-1, 8), 1, 1)
+    u1 = O.bootstrap(t1[0], t1[1], keys.bk, None)
+    assert (u1[0] == g['mux_u1_a']).all() and (u1[1] == g['mux_u1_b']).all()
+    mux = O.gate_mux(m[0], m[1], m[2], keys.bk, keys.ks)
+    assert (mux[0] == g['mux_a']).all() and (mux[1] == g['mux_b']).all()
+
+
 def test_all_gates_truth_tables(keys):
     a_bits = numpy.array(G.GATE_BITS_A)
     b_bits = numpy.array(G.GATE_BITS_B)

@@ -64,9 +64,14 @@ def ff_canon_dev(v0, v1):
     return ff_add_keps(v0, v1, e['f'])
 
 
+def ff_reduce_limbs_nc(l, m, h0, h1):
+    e = run('ff_reduce_limbs_nc', l=l, m=m, h0=h0, h1=h1)
+    return e['r0'] | (e['r1'] << 32)
+
+
 def ff_reduce_limbs(l, m, h0, h1):
-    e = run('ff_reduce_limbs', l=l, m=m, h0=h0, h1=h1)
-    return ff_canon_dev(e['r0'], e['r1'])
+    v = ff_reduce_limbs_nc(l, m, h0, h1)
+    return ff_canon_dev(v & M32, v >> 32)
 
 
 def mul128(a, b):
@@ -153,7 +158,7 @@ def in_range(v):
 
 def test_parser_sees_every_device_sequence():
     for fn, n in (('ff_sub_dev', 2), ('mul128', 1), ('mac128', 1), ('ff_add_keps', 1), ('ff_canon_dev', 1),
-                  ('ff_reduce_limbs', 1), ('ff_comb_a', 1), ('ff_comb_b', 1), ('mulwide', 1)):
+                  ('ff_reduce_limbs_nc', 1), ('ff_comb_a', 1), ('ff_comb_b', 1), ('mulwide', 1)):
         assert len(blocks(fn)) == n, fn
 
 
@@ -198,6 +203,11 @@ def test_reduce_limbs_all_edge_limbs():
                     got = ff_reduce_limbs(l, m, h0, h1)
                     want = (l + m * phi + h0 * phi ** 2 + h1 * phi ** 3) % P
                     assert in_range(got) and got % P == want, (l, m, h0, h1, hex(got))
+                    # the uncanonicalised form: any 64-bit value of the right residue, and the rare-path trigger
+                    # (high limb all ones) fires whenever it lies above p
+                    nc = ff_reduce_limbs_nc(l, m, h0, h1)
+                    assert 0 <= nc < 1 << 64 and nc % P == want
+                    assert nc <= P or nc >> 32 == M32
     for _ in range(3000):
         l, m, h0, h1 = (RNG.randrange(1 << 32) for _ in range(4))
         got = ff_reduce_limbs(l, m, h0, h1)

@@ -84,6 +84,7 @@ def main():
                          'blind_rotate_kernelINS_5BrCfgILi1ELi256)')
     ap.add_argument('--by-func', action='store_true', help='also split each phase by innermost ff.cuh / br_phases function')
     ap.add_argument('--opcodes', action='store_true', help='per-step histogram of instruction forms (carry-out variants split)')
+    ap.add_argument('--json', action='store_true', help='print one JSON object with the per-step totals (used by bench.py)')
     args = ap.parse_args()
 
     tmp = tempfile.mkdtemp()
@@ -111,6 +112,24 @@ def main():
     # lines of br_phases.cuh inside a `switch (g)` (warp-uniform 4-way): each branch runs for a quarter of the warps
     bpath = os.path.join(ROOT, 'nufhe_b200', 'csrc', 'br_phases.cuh')
     case_lines = {i for i, l in enumerate(open(bpath).read().splitlines(), 1) if re.match(r'\s*(case \d+|default):', l)}
+
+    # lines of br_phases.cuh inside an `if (canon_needed(...)) { ... }` block: the rare path of the deferred
+    # canonicalisation (taken with probability ~2^-28 per task) -- not part of the executed step
+    rare_lines = set()
+    bsrc = open(bpath).read().splitlines()
+    for i, l in enumerate(bsrc, 1):
+        if 'if (canon_needed(' in l:
+            depth, j = 0, i
+            while True:
+                depth += bsrc[j - 1].count('{') - bsrc[j - 1].count('}')
+                rare_lines.add(j)
+                if depth <= 0 and j > i:
+                    break
+                if depth <= 0 and '{' not in bsrc[j - 1]:
+                    rare_lines.add(j + 1)     # single-statement body on the next line
+                    break
+                j += 1
+            rare_lines.discard(i)             # the test itself is executed
 
     fn_maps = {}
 
@@ -157,6 +176,9 @@ def main():
         if phase != 'other' and not in_loop:
             phase = 'plain:' + phase     # the non-rotating instantiation (nb_external_product)
         w = 0.25 if any(path.endswith('br_phases.cuh') and line in case_lines for path, line in chain) else 1
+        if any(path.endswith('br_phases.cuh') and line in rare_lines for path, line in chain):
+            counts['rare:' + phase][pipe] += w
+            continue
         counts[phase][pipe] += w
         if args.opcodes and phase.startswith('phase_'):
             forms[instruction_form(op, m.group(2))] += w * (
@@ -174,6 +196,17 @@ def main():
 
     # the wide shape (1 ciphertext on 256 threads) runs the forward phases in one sweep
     mult = dict(STEP_MULT, phase_fwd1=1, phase_fwd2=1, phase_fwd3=1) if 'BrCfgILi1E' in args.kernel else STEP_MULT
+    if args.json:
+        import json
+        tot = collections.Counter()
+        for phase, c in counts.items():
+            if phase.startswith('phase_'):
+                for k, v in c.items():
+                    tot[k] += v * mult.get(phase, 1)
+        print(json.dumps({'kernel': args.kernel, 'per_thread_step': {k: tot[k] for k in ('alu', 'fma', 'lsu', 'uni', 'other')},
+                          'per_thread_step_total': sum(tot.values()),
+                          'phases': {ph: sum(c.values()) * mult.get(ph, 1) for ph, c in counts.items() if ph.startswith('phase_')}}))
+        return 0
     print('%-22s %7s %7s %7s %7s %7s %8s' % ('phase (static)', 'alu', 'fma', 'lsu', 'uni', 'other', 'total'))
     tot = collections.Counter()
     for phase in sorted(counts):

@@ -44,7 +44,8 @@ def time_ms(fn, reps):
 
 
 out = {'gate_nand': [], 'gate_mux': [], 'ntt': [], 'hbm_peak_gbs': peak, 'build': thr.build_info()}
-for B in (1, 64, 256, 592, 1024, 4096, 16384, 65536):
+BATCHES = [int(x) for x in os.environ.get('SWEEP_BATCHES', '1,64,256,592,768,1024,1536,2048,4096,16384,65536').split(',')]
+for B in BATCHES:
     x, y = rand_ct(B), rand_ct(B)
     dest = vm.empty_ciphertext((B,))
     ms = time_ms(lambda: vm.gate_nand(x, y, dest=dest), 5 if B <= 4096 else 2)
