@@ -37,6 +37,11 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out);
 void nb_ctx_destroy(nb_ctx *ctx);
 const char *nb_last_error(const nb_ctx *ctx);
 int nb_ctx_set_stream(nb_ctx *ctx, void *stream);
+/* Pre-allocate the context's scratch (work queue and parked accumulators of the fused bootstrap, variance block sums
+ * of the key switch) for launches of up to `batch` ciphertexts.  Calls within that size then allocate nothing, which
+ * is what CUDA-graph capture of a gate circuit needs (reference counterpart: Reikna plans allocate their temporaries
+ * when a computation is compiled, blind_rotate.py:245-246). */
+int nb_ctx_reserve(nb_ctx *ctx, size_t batch);
 int nb_ctx_synchronize(nb_ctx *ctx);          /* thread.synchronize() */
 /* Library / device facts: sm count, kernel register counts etc. as a short text (for bench/profiles). */
 const char *nb_build_info(void);

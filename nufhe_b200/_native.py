@@ -26,6 +26,7 @@ SIGNATURES = {
     'nb_last_error': [_vp],
     'nb_ctx_set_stream': [_vp, _vp],
     'nb_ctx_synchronize': [_vp],
+    'nb_ctx_reserve': [_vp, _sz],
     'nb_build_info': [],
     'nb_ntt_forward_i32': [_vp, _vp, _vp, _sz],
     'nb_ntt_forward_u64': [_vp, _vp, _vp, _sz],

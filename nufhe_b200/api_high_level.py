@@ -162,6 +162,12 @@ class VirtualMachine:
         gate_func(self.thread, self.cloud_key, dest, *args, perf_params=self.perf_params)
         return dest
 
+    def capture(self, circuit, reserve_batch=None):
+        """Record `circuit()` -- any sequence of this VM's gates on device-resident ciphertexts -- into a CUDA graph;
+        returns a `GateGraph` whose `replay()` re-runs the whole circuit with one launch (nufhe_b200/graph.py)."""
+        from .graph import GateGraph
+        return GateGraph(self.thread, circuit, reserve_batch=reserve_batch)
+
     def __getattr__(self, name):
         if name.startswith('gate_'):
             return lambda *args, **kwds: self._gate(name, *args, **kwds)

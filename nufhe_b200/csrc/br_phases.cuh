@@ -63,17 +63,27 @@ constexpr int POLY_STRIDE = 16 * ROW_STRIDE;      // u64 per work polynomial
 //   BrCfg<1, 256> ("wide"):  256 threads per ciphertext: the forward phases take one sweep instead of two and the
 //                            inverse phases leave half of the warps idle; 36 % fewer instructions on the critical
 //                            path of a step.  Used when the batch fits one wave of such CTAs (latency, not throughput).
-template <int CT_, int THREADS_> struct BrCfg {
+template <int CT_, int THREADS_, int CTAS_ = 512 / THREADS_, bool TWD_GLOBAL_ = false> struct BrCfg {
     static constexpr int CT = CT_, THREADS = THREADS_;
     static constexpr int POLYS = 4 * CT;                       // work polynomials per CTA
     static constexpr int FWD_SWEEPS = 256 * CT / THREADS;      // sweeps of the forward phases
     static constexpr int INV_TASKS = 128 * CT;                 // threads with work in the inverse phases
-    static constexpr int CTAS_PER_SM = 512 / THREADS;          // 128 registers per thread: 16 warps per SM
+    static constexpr int CTAS_PER_SM = CTAS_;                  // default 512 / THREADS: 16 warps per SM at 128 registers
+    static constexpr bool TWD_GLOBAL = TWD_GLOBAL_;            // twiddle tables read from global memory / L1, not staged
     static_assert(FWD_SWEEPS >= 1 && FWD_SWEEPS * THREADS == 256 * CT && INV_TASKS <= THREADS && THREADS % 128 == 0, "shape");
 };
+#ifndef NB_BR_THREADS
+#define NB_BR_THREADS (128 * NB_BR_CT)
+#endif
+#ifndef NB_BR_CTAS
+#define NB_BR_CTAS (512 / NB_BR_THREADS)
+#endif
+#ifndef NB_BR_TWD_GLOBAL
+#define NB_BR_TWD_GLOBAL 0
+#endif
 constexpr int BR2_CT = NB_BR_CT;                  // ciphertexts per CTA of the default shape (1, 2 or 4)
-constexpr int BR2_THREADS = 128 * BR2_CT;
-using BrDefault = BrCfg<BR2_CT, BR2_THREADS>;
+constexpr int BR2_THREADS = NB_BR_THREADS;
+using BrDefault = BrCfg<BR2_CT, BR2_THREADS, NB_BR_CTAS, NB_BR_TWD_GLOBAL != 0>;
 using BrWide = BrCfg<1, 256>;
 constexpr int BR2_POLYS = BrDefault::POLYS;
 // Engine bootstrap-key row: 8 planes [(mi*2+j)*2+mo][row*64 + stored column] of plain field values plus
@@ -336,10 +346,17 @@ NB_HD void phase_inv3(int p, int row, int u, u64 *w_all)
 template <int CT> NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64 *bk_row)
 {
     const int pos = row * 64 + 2 * q;
+#ifdef NB_BK_L1_BOUND
+    // TIMING EXPERIMENT ONLY (wrong results): every key load hits the same 5 KB, i.e. the L1 -- the time a perfect
+    // shared-memory / TMA staging of the key row could at best reach (profiles/r2_variants.md, N1 decision)
+    const int kpos = pos & 63;
+#else
+    const int kpos = pos;
+#endif
     u64 bk[BK_PLANES][2];
     static_for<0, BK_PLANES>([&](auto M) {
         constexpr int m = decltype(M)::value;            // m = (mi * 2 + j) * 2 + mo; 8 + mo = correction
-        ld2_global(bk_row + m * NTT_N + pos, bk[m][0], bk[m][1]);
+        ld2_global(bk_row + m * NTT_N + kpos, bk[m][0], bk[m][1]);
     });
     for (int ct = 0; ct < CT; ct++) {
         u64 *w = w_all + ct * 4 * POLY_STRIDE + row * ROW_STRIDE + 2 * q;

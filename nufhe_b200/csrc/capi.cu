@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/nufhe_b200.h"
 #include "kernels.cuh"
 #include "tables.h"
@@ -64,6 +65,13 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
+// NVTX range around the launches of one entry point (prologue + blind rotation, key switch, transforms, ...): shows up
+// in Nsight Systems / `ncu --nvtx`; a no-op costing two library calls when no tool is attached (nvtx3 is header-only).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 #define NB_ON_DEVICE(ctx)                   \
     DeviceGuard _guard((ctx)->device);      \
     NB_TRY(check(ctx, _guard.err, "cudaSetDevice"))
@@ -92,7 +100,7 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
         e = getenv("NUFHE_B200_FORCE_CHUNKS");
         ctx->force_chunks = e ? atoi(e) : 0;
         e = getenv("NUFHE_B200_STAGGER");
-        ctx->stagger_cycles = e ? atoi(e) : 24000;        // about half a CMux step of the throughput shape
+        ctx->stagger_cycles = e ? atoi(e) : 12000;        // about a quarter of a CMux step (measured best of 0 / 12k / 24k / 36k)
     }
     if (const char *e = getenv("NUFHE_B200_FORCE_RARE_PATH")) {
         // test knob: run the canonicalisation fix-up of the deferred-canonicalisation phases on every task
@@ -115,6 +123,8 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
                                            (int)br_smem_bytes<BrDefault>()), "cudaFuncSetAttribute(blind_rotate)"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel<BrWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)br_smem_bytes<BrWide>()), "cudaFuncSetAttribute(blind_rotate wide)"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)KS_SMEM_BYTES), "cudaFuncSetAttribute(keyswitch)"));
     {   // batches that fit one wave of wide CTAs (one ciphertext on 256 threads) take the low-latency shape
         const char *e = getenv("NUFHE_B200_WIDE_MAX");
         // up to one wave the wide shape has the shortest step; between one and ~1.7 waves it still wins, time-sliced
@@ -178,7 +188,7 @@ const char *nb_build_info(void)
 static int ntt_grid(nb_ctx *ctx, size_t batch)
 {
     size_t blocks = (batch + NTT_SWEEP_POLYS - 1) / NTT_SWEEP_POLYS;
-    size_t cap = (size_t)ctx->sm_count * 2;       // persistent: 2 CTAs per SM, grid-stride over the batch
+    size_t cap = (size_t)ctx->sm_count * NTT_CTAS;   // persistent: NTT_CTAS CTAs per SM, grid-stride over the batch
     return (int)(blocks < cap ? blocks : cap);
 }
 
@@ -188,6 +198,7 @@ int nb_ntt_forward_i32(nb_ctx *ctx, const int32_t *in, uint64_t *out, size_t bat
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_i32: null argument");
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:ntt_forward");
     ntt_forward_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, ntt_smem_bytes(NTT_RAW_I32_BYTES), ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<i32>");
 }
@@ -198,6 +209,7 @@ int nb_ntt_forward_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_forward_u64: null argument");
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:ntt_forward");
     ntt_forward_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, ntt_smem_bytes(NTT_RAW_U64_BYTES), ctx->stream>>>(in, (u64 *)out, ctx->d_ph_fwd, batch);
     return launch_check(ctx, "ntt_forward_kernel<u64>");
 }
@@ -208,6 +220,7 @@ int nb_ntt_inverse_i32(nb_ctx *ctx, const uint64_t *in, int32_t *out, size_t bat
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_i32: null argument");
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:ntt_inverse");
     ntt_inverse_kernel<true><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, ntt_smem_bytes(NTT_RAW_U64_BYTES), ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<i32>");
 }
@@ -218,6 +231,7 @@ int nb_ntt_inverse_u64(nb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t ba
     if (batch == 0) return NB_OK;
     if (!in || !out) return fail(ctx, NB_EINVAL, "nb_ntt_inverse_u64: null argument");
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:ntt_inverse");
     ntt_inverse_kernel<false><<<ntt_grid(ctx, batch), NTT_SWEEP_THREADS, ntt_smem_bytes(NTT_RAW_U64_BYTES), ctx->stream>>>((const u64 *)in, out, ctx->d_ph_inv, batch);
     return launch_check(ctx, "ntt_inverse_kernel<u64>");
 }
@@ -243,6 +257,7 @@ int nb_bk_prepare(nb_ctx *ctx, const uint64_t *bk_ref, uint64_t *bk_int, size_t 
     if (!ctx || !bk_ref || !bk_int) return fail(ctx, NB_EINVAL, "nb_bk_prepare: null argument");
     if (rows == 0) return NB_OK;
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:bk_prepare");
     size_t total = rows * NTT_N, blocks = (total + 255) / 256, cap = (size_t)ctx->sm_count * 16;
     bk_prepare_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>((const u64 *)bk_ref, (u64 *)bk_int,
                                                                                   ctx->d_ones512, rows);
@@ -253,7 +268,7 @@ int nb_bk_prepare(nb_ctx *ctx, const uint64_t *bk_ref, uint64_t *bk_int, size_t 
 
 // Chunks per chain for `chains` chains on `slots` resident CTAs (kernels.cuh: blind_rotate_kernel).  One wave or
 // less needs no slicing.  Otherwise the launch takes ceil(chains * C / slots) rounds of ceil(n / C) steps; each chunk
-// also pays for parking / fetching the accumulators and refilling the pipeline (about a third of a step).
+// also pays for parking / fetching the accumulators (measured: below the noise, profiles/r2_variants.md; 0.1 step here).
 static int pick_chunks(size_t chains, size_t slots, int n, int max_chunks)
 {
     if (chains <= slots || n <= 1 || max_chunks <= 1) return 1;
@@ -263,7 +278,7 @@ static int pick_chunks(size_t chains, size_t slots, int n, int max_chunks)
         const int steps = (n + c - 1) / c;
         const int chunks = (n + steps - 1) / steps;
         const double rounds = (double)((chains * (size_t)chunks + slots - 1) / slots);
-        const double cost = rounds * (steps + 0.35);
+        const double cost = rounds * (steps + 0.1);
         if (c == 1 || cost < best_cost * 0.995) { best = chunks; best_cost = cost; }
     }
     return best;
@@ -295,10 +310,12 @@ template <class Cfg> static int launch_br_cfg(nb_ctx *ctx, BlindRotateArgs &p)
     size_t grid = chains;
     if (chains > slots) {
         // more than one wave: persistent CTAs pull (chain, chunk) tickets
-        NB_TRY(reserve_words(ctx, (void **)&ctx->d_sched, &ctx->sched_words, BR_SCHED_HEADER + chains, sizeof(unsigned)));
+        // ready queue: head, tail, then one entry per (chain, chunk); entries of first chunks stay 0 (implicit)
+        const size_t entries = chunks > 1 ? chains * (size_t)chunks : 0;
+        NB_TRY(reserve_words(ctx, (void **)&ctx->d_sched, &ctx->sched_words, BR_SCHED_HEADER + entries, sizeof(unsigned)));
         if (chunks > 1)
             NB_TRY(reserve_words(ctx, (void **)&ctx->d_state, &ctx->state_words, chains * Cfg::CT * 2 * NTT_N, sizeof(int32_t)));
-        NB_TRY(check(ctx, cudaMemsetAsync(ctx->d_sched, 0, (BR_SCHED_HEADER + chains) * sizeof(unsigned), ctx->stream), "cudaMemsetAsync"));
+        NB_TRY(check(ctx, cudaMemsetAsync(ctx->d_sched, 0, (BR_SCHED_HEADER + entries) * sizeof(unsigned), ctx->stream), "cudaMemsetAsync"));
         p.sched = ctx->d_sched; p.state = ctx->d_state;
         grid = slots;
     }
@@ -316,11 +333,24 @@ static int launch_br(nb_ctx *ctx, BlindRotateArgs &p)
 
 extern "C" {
 
+int nb_ctx_reserve(nb_ctx *ctx, size_t batch)
+{
+    if (!ctx) return NB_EINVAL;
+    NB_ON_DEVICE(ctx);
+    // everything launch_br_cfg / nb_keyswitch could ask for with up to `batch` ciphertexts (2 * batch for gate_mux's
+    // double launch is the caller's business): after this, those calls never allocate, so they can be captured
+    NB_TRY(reserve_words(ctx, (void **)&ctx->d_sched, &ctx->sched_words, BR_SCHED_HEADER + (batch + 1) * (size_t)ctx->max_chunks, sizeof(unsigned)));
+    NB_TRY(reserve_words(ctx, (void **)&ctx->d_state, &ctx->state_words, (batch + 2) * 2 * NTT_N, sizeof(int32_t)));
+    NB_TRY(reserve_words(ctx, (void **)&ctx->d_cv_blocks, &ctx->cv_words, batch * KS_CV_BLOCKS, sizeof(float)));
+    return NB_OK;
+}
+
 int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, size_t bk_row, size_t batch)
 {
     if (!ctx || !accum || !bk_int) return fail(ctx, NB_EINVAL, "nb_external_product: null argument");
     if (batch == 0) return NB_OK;
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:external_product");
     BlindRotateArgs p{};
     p.accum = accum; p.accum_out = accum; p.bk = (const u64 *)bk_int + bk_row * BK_ROW_U64;
     p.plain = 1; p.batch = batch;
@@ -333,6 +363,7 @@ static int launch_blind_rotate(nb_ctx *ctx, BlindRotateArgs &p)
     if (p.n <= 0 || p.n > LWE_N_MAX) return fail(ctx, NB_EUNSUPPORTED, "LWE dimension out of range");
     if (p.batch == 0) return NB_OK;
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:gate_prologue+blind_rotate+extract");
     NB_TRY(launch_br(ctx, p));
     return launch_check(ctx, "blind_rotate_kernel");
 }
@@ -392,13 +423,12 @@ int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, cons
     if (t < 1 || log2_base < 1 || t * log2_base > 31) return fail(ctx, NB_EINVAL, "nb_keyswitch: bad decomposition");
     if (batch == 0) return NB_OK;
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:keyswitch");
     KeyswitchArgs p{};
     p.src1_a = src1_a; p.src1_b = src1_b; p.src2_a = src2_a; p.src2_b = src2_b; p.c = c;
     p.ks_a = ks_a; p.ks_b = ks_b; p.ks_cv = ks_cv; p.res_a = res_a; p.res_b = res_b; p.res_cv = res_cv;
     p.in_size = (int)in_size; p.n = (int)n; p.t = t; p.log2_base = log2_base; p.batch = batch;
     if (t == 8 && log2_base == 2 && in_size == (size_t)KS_IN && n == (size_t)KS_N) {
-        NB_TRY(check(ctx, cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)KS_SMEM_BYTES), "cudaFuncSetAttribute(keyswitch)"));
         // The consumer loop always walks KS_TILE ciphertext slots, so a CTA costs the same whatever its tile:
         // fill the tiles, then split the 1024 input coefficients over blockIdx.y until the SMs are covered
         // (partial sums meet in integer atomics).  One ciphertext: 128 CTAs x 8 coefficients.
@@ -550,6 +580,7 @@ int nb_lwe_dot(nb_ctx *ctx, int32_t *out, const int32_t *a, const int32_t *key, 
     if (n == 0 || n > (1u << 30)) return fail(ctx, NB_EINVAL, "nb_lwe_dot: bad LWE dimension");
     if (batch == 0) return NB_OK;
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:lwe_dot");
     size_t blocks = (batch * 32 + 255) / 256, cap = (size_t)ctx->sm_count * 16;
     lwe_dot_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(out, a, key, add1, add2, sign, batch, (int)n);
     return launch_check(ctx, "lwe_dot_kernel");
@@ -565,6 +596,7 @@ int nb_make_keyswitch_key(nb_ctx *ctx, int32_t *ks_a, int32_t *ks_b, float *ks_c
     if (t < 1 || log2_base < 1 || t * log2_base > 31 || n == 0) return fail(ctx, NB_EINVAL, "nb_make_keyswitch_key: bad decomposition");
     if (in_size == 0) return NB_OK;
     NB_ON_DEVICE(ctx);
+    NvtxRange nvtx_range("nufhe_b200:make_keyswitch_key");
     const size_t rows = in_size * (size_t)t << log2_base;
     size_t blocks = (rows * 32 + 255) / 256, cap = (size_t)ctx->sm_count * 16;
     make_keyswitch_key_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(

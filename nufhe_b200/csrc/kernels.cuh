@@ -37,11 +37,17 @@ template <int N> NB_D void cp_async_wait() { asm volatile("cp.async.wait_group %
 //     those four elements sit in two 16-byte shared-memory words 8 rows apart (ntt_pair_position), so the u64 side is
 //     moved with 128-bit shared AND 128-bit global accesses (512 contiguous bytes per warp), bank-conflict free;
 //   * the int32 side is read from / written to global memory as 128-byte warp rows (x[64 j1 + j2], lanes = j2).
+#ifndef NB_NTT_CTAS
+#define NB_NTT_CTAS 3                      // resident CTAs per SM of the stand-alone transforms (2: -3.6 %, profiles/r2_variants.md)
+#endif
+constexpr int NTT_CTAS = NB_NTT_CTAS;
 constexpr int NTT_RAW_I32_BYTES = NTT_SWEEP_POLYS * NTT_N * (int)sizeof(i32);
 constexpr int NTT_RAW_U64_BYTES = NTT_SWEEP_POLYS * NTT_N * (int)sizeof(u64);
-constexpr size_t ntt_smem_bytes(int raw_bytes)
+// staging buffers per CTA: two (prefetch one sweep ahead) unless three CTAs of u64 input have to share the SM
+NB_HDC int ntt_raw_buffers(int raw_bytes) { return (NTT_CTAS > 2 && raw_bytes > NTT_RAW_I32_BYTES) ? 1 : 2; }
+NB_HDC size_t ntt_smem_bytes(int raw_bytes)
 {
-    return (size_t)NTT_SWEEP_POLYS * POLY_STRIDE * sizeof(u64) + NTT_N * sizeof(u64) + 2 * (size_t)raw_bytes;
+    return (size_t)NTT_SWEEP_POLYS * POLY_STRIDE * sizeof(u64) + NTT_N * sizeof(u64) + ntt_raw_buffers(raw_bytes) * (size_t)raw_bytes;
 }
 
 // shared-memory position (in u64) of natural element k = 2 t of a polynomial, t = threadIdx.x in [0, 256): the
@@ -67,7 +73,7 @@ template <int POLY_BYTES> NB_D void ntt_stage(unsigned char *raw, const unsigned
 }
 
 template <bool IN_I32>
-__global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_forward_kernel(const void *__restrict__ in, u64 *__restrict__ out,
+__global__ void __launch_bounds__(NTT_SWEEP_THREADS, NTT_CTAS) ntt_forward_kernel(const void *__restrict__ in, u64 *__restrict__ out,
                                                                             const u64 *__restrict__ twd_g, size_t batch)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -82,11 +88,16 @@ __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_forward_kernel(const
     cp_async_commit();
     for (int i = tid; i < NTT_N; i += NTT_SWEEP_THREADS) twd[i] = twd_g[i];
     const int pos = ntt_pair_position(tid);
+    constexpr int NBUF = ntt_raw_buffers(RAW_BYTES);
     int buf = 0;
-    for (; p0 < batch; p0 += stride, buf ^= 1) {
-        if (p0 + stride < batch) ntt_stage<POLY_BYTES>(raw + (buf ^ 1) * RAW_BYTES, (const unsigned char *)in, p0 + stride, batch, tid);
-        cp_async_commit();
-        cp_async_wait<1>();                       // everything but the group just committed has landed
+    for (; p0 < batch; p0 += stride, buf ^= (NBUF - 1)) {
+        if (NBUF == 2) {
+            if (p0 + stride < batch) ntt_stage<POLY_BYTES>(raw + (buf ^ 1) * RAW_BYTES, (const unsigned char *)in, p0 + stride, batch, tid);
+            cp_async_commit();
+            cp_async_wait<1>();                   // everything but the group just committed has landed
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
         {   // pass 1: thread = (poly, j2), reads x[64 j1 + j2] from the staging buffer
             const int pl = tid >> 6, j2 = tid & 63;
@@ -106,6 +117,10 @@ __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_forward_kernel(const
         __syncthreads();
         { const int g = tid >> 6, x = tid & 63; phase_fwd2(x >> 4, x & 15, g, w); }
         __syncthreads();
+        if (NBUF == 1 && p0 + stride < batch) {   // single staging buffer: refill it now that pass 1 has consumed it
+            ntt_stage<POLY_BYTES>(raw, (const unsigned char *)in, p0 + stride, batch, tid);
+            cp_async_commit();
+        }
         { const int u = tid & 3, r = (tid >> 2) & 15, p = tid >> 6; phase_fwd3(p, r, u, w); }
         __syncthreads();
         // natural-order store: 16 bytes = elements (2t, 2t+1) and (2t+512, 2t+513) of each polynomial
@@ -126,7 +141,7 @@ __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_forward_kernel(const
 }
 
 template <bool OUT_I32>
-__global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_inverse_kernel(const u64 *__restrict__ in, void *__restrict__ out,
+__global__ void __launch_bounds__(NTT_SWEEP_THREADS, NTT_CTAS) ntt_inverse_kernel(const u64 *__restrict__ in, void *__restrict__ out,
                                                                             const u64 *__restrict__ twd_g, size_t batch)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -141,11 +156,16 @@ __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_inverse_kernel(const
     cp_async_commit();
     for (int i = tid; i < NTT_N; i += NTT_SWEEP_THREADS) twd[i] = twd_g[i];
     const int pos = ntt_pair_position(tid);
+    constexpr int NBUF = ntt_raw_buffers(RAW_BYTES);
     int buf = 0;
-    for (; p0 < batch; p0 += stride, buf ^= 1) {
-        if (p0 + stride < batch) ntt_stage<POLY_BYTES>(raw + (buf ^ 1) * RAW_BYTES, (const unsigned char *)in, p0 + stride, batch, tid);
-        cp_async_commit();
-        cp_async_wait<1>();
+    for (; p0 < batch; p0 += stride, buf ^= (NBUF - 1)) {
+        if (NBUF == 2) {
+            if (p0 + stride < batch) ntt_stage<POLY_BYTES>(raw + (buf ^ 1) * RAW_BYTES, (const unsigned char *)in, p0 + stride, batch, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
         // natural order -> pass layout (the mirror image of the forward kernel's store), canonicalising on the way
 #pragma unroll
@@ -156,6 +176,10 @@ __global__ void __launch_bounds__(NTT_SWEEP_THREADS, 2) ntt_inverse_kernel(const
             st2(w + pl * POLY_STRIDE + pos + 8 * ROW_STRIDE, ff_canon(lo.y), ff_canon(hi.y));
         }
         __syncthreads();
+        if (NBUF == 1 && p0 + stride < batch) {   // single staging buffer: refill it now that it has been consumed
+            ntt_stage<POLY_BYTES>(raw, (const unsigned char *)in, p0 + stride, batch, tid);
+            cp_async_commit();
+        }
         { const int u = tid & 3, r = (tid >> 2) & 15, p = tid >> 6; phase_inv3(p, r, u, w); }
         __syncthreads();
         { const int g = tid >> 6, x = tid & 63; phase_inv2(x >> 4, x & 15, g, w); }
@@ -244,7 +268,7 @@ NB_HD i32 modswitch_2n(i32 x) { return (i32)(((u32)x + (1u << 20)) >> 21); }
 template <class Cfg> constexpr size_t br_smem_bytes()
 {
     return (size_t)Cfg::CT * 2 * NTT_N * sizeof(i32) + (size_t)Cfg::POLYS * POLY_STRIDE * sizeof(u64) +
-           2 * NTT_N * sizeof(u64) + 64;
+           (Cfg::TWD_GLOBAL ? 0 : 2 * NTT_N * sizeof(u64)) + 64;
 }
 constexpr size_t BR2_SMEM_BYTES = br_smem_bytes<BrDefault>();
 
@@ -269,7 +293,7 @@ struct BlindRotateArgs {
     size_t batch;
     // work queue (see blind_rotate_kernel): `chains` groups of Cfg::CT ciphertexts, each cut into `chunks` runs of
     // `steps_per_chunk` CMux steps.  sched == null: one chain per CTA, no queue (single wave).
-    unsigned *sched;        // [0] = next ticket, [BR_SCHED_HEADER + chain] = chunks of the chain completed so far
+    unsigned *sched;        // [0] = queue head, [1] = entries appended so far, [BR_SCHED_HEADER + t] = entry t of the ready queue
     i32 *state;             // accumulators parked between the chunks of a chain: (chains * CT, 2, 1024)
     unsigned chains, chunks;
     int steps_per_chunk;
@@ -290,8 +314,8 @@ template <class Cfg> NB_D Br2Smem br2_carve(unsigned char *raw)
     Br2Smem s;
     s.w = reinterpret_cast<u64 *>(raw);
     s.twd_fwd = s.w + Cfg::POLYS * POLY_STRIDE;
-    s.twd_inv = s.twd_fwd + NTT_N;
-    s.acc = reinterpret_cast<i32 *>(s.twd_inv + NTT_N);
+    s.twd_inv = s.twd_fwd + (Cfg::TWD_GLOBAL ? 0 : NTT_N);
+    s.acc = reinterpret_cast<i32 *>(s.twd_inv + (Cfg::TWD_GLOBAL ? 0 : NTT_N));
     s.rot = reinterpret_cast<int *>(s.acc + Cfg::CT * 2 * NTT_N);
     return s;
 }
@@ -346,22 +370,32 @@ NB_D void st_release_u32(unsigned *p, unsigned v)
 }
 
 // The kernel is persistent: the grid is at most one wave of resident CTAs (Cfg::CTAS_PER_SM per SM) and every CTA
-// pulls work items from a ticket counter until none are left.  A work item is one CHUNK of one CHAIN: a chain is the
-// whole blind rotation of Cfg::CT ciphertexts, a chunk `steps_per_chunk` consecutive CMux steps of it.  Tickets run
-// chunk-major (all first chunks, then all second chunks, ...), so a batch that is not a multiple of the wave size is
-// time-sliced over all SMs instead of leaving a partial last wave: 1024 ciphertexts take 1.73 wave-times instead of
-// 2 (the host picks the chunk count, capi.cu: pick_chunks).  Between chunks the accumulators (8 KB per ciphertext)
-// are parked in global memory; chunk c of a chain waits for the chain's progress counter to reach c -- its
-// predecessor holds a lower ticket, i.e. belongs to a CTA that is already running, so the wait cannot deadlock.
+// pulls work items from a queue until none are left.  A work item is one CHUNK of one CHAIN: a chain is the whole
+// blind rotation of Cfg::CT ciphertexts, a chunk `steps_per_chunk` consecutive CMux steps of it.  Cutting chains into
+// chunks time-slices a batch that is not a multiple of the wave size over all SMs instead of leaving a partial last
+// wave: 1024 ciphertexts take 1.73 wave-times instead of 2 (the host picks the chunk count, capi.cu: pick_chunks).
+// Between chunks the accumulators (8 KB per ciphertext) are parked in global memory.
+// The queue is a FIFO of READY chains in global memory: entry t (t = 0 .. chains * chunks - 1) holds 1 + chain +
+// chains * chunk; the host memset leaves every entry 0 = "not written yet" and the kernel treats entries t < chains as
+// the initial state (chain t, chunk 0).  A CTA takes the next entry with an atomic increment of the head and waits for
+// that entry to be written; when it finishes a chunk that is not the chain's last, it parks the accumulators and
+// appends the chain's next chunk at the tail (release).  Whoever pops it (acquire) finds the accumulators.  An entry
+// a CTA waits for is always produced by a chunk that is running on another resident CTA, so the wait cannot deadlock,
+// and a ready chain never waits behind an unready one -- with in-order tickets and per-chain progress counters, which
+// this replaces, 300 chains on 296 CTAs lost 18 % to such head-of-line waits (profiles/r2_variants.md).
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g,
                                                                        const u64 *__restrict__ twd_inv_g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Br2Smem s = br2_carve<Cfg>(smem_raw);
-    __shared__ unsigned s_item;
+    Br2Smem s = br2_carve<Cfg>(smem_raw);
+    __shared__ unsigned s_item, s_entry;
     const int tid = threadIdx.x;
-    for (int i = tid; i < NTT_N; i += Cfg::THREADS) { s.twd_fwd[i] = twd_fwd_g[i]; s.twd_inv[i] = twd_inv_g[i]; }
+    if (Cfg::TWD_GLOBAL) {
+        s.twd_fwd = const_cast<u64 *>(twd_fwd_g); s.twd_inv = const_cast<u64 *>(twd_inv_g);
+    } else {
+        for (int i = tid; i < NTT_N; i += Cfg::THREADS) { s.twd_fwd[i] = twd_fwd_g[i]; s.twd_inv[i] = twd_inv_g[i]; }
+    }
     const unsigned total = p.chains * p.chunks;
     constexpr int ACC_WORDS = Cfg::CT * 2 * NTT_N;
     // Two CTAs share an SM.  In a single-wave launch they would march through the phases in lock step (the MAC is
@@ -384,7 +418,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_k
             item = s_item;
         }
         if (item >= total) break;
-        const unsigned chunk = item / p.chains, chain = item - chunk * p.chains;
+        unsigned chunk = 0, chain = item;
+        if (p.sched && item >= p.chains) {
+            // entries beyond the initial ones are appended by the CTAs that finish chunks
+            if (tid == 0) {
+                unsigned e;
+                while ((e = ld_acquire_u32(p.sched + BR_SCHED_HEADER + item)) == 0) __nanosleep(100);
+                s_entry = e - 1;
+            }
+            __syncthreads();
+            const unsigned e = s_entry;
+            chunk = e / p.chains; chain = e - chunk * p.chains;
+        }
         const size_t ct0 = (size_t)chain * Cfg::CT;
         // ciphertext slots beyond the batch replay the last ciphertext and store nothing
         auto ct_of = [&](int slot) { size_t c = ct0 + slot; return c < p.batch ? c : p.batch - 1; };
@@ -416,11 +461,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_k
                 s.acc[e] = val;
             }
         } else {
-            // resume a parked chain: wait until its previous chunk has been published, then fetch the accumulators
-            if (tid == 0) {
-                while (ld_acquire_u32(p.sched + BR_SCHED_HEADER + chain) < chunk) __nanosleep(200);
-            }
-            __syncthreads();
+            // resume a parked chain: its queue entry was published after the accumulators (release / acquire above)
             const int4 *src = reinterpret_cast<const int4 *>(p.state + (size_t)chain * ACC_WORDS);
             for (int e = tid; e < ACC_WORDS / 4; e += Cfg::THREADS) reinterpret_cast<int4 *>(s.acc)[e] = __ldcg(src + e);
         }
@@ -447,7 +488,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_k
             for (int e = tid; e < ACC_WORDS / 4; e += Cfg::THREADS) __stcg(dst + e, reinterpret_cast<const int4 *>(s.acc)[e]);
             __threadfence();
             __syncthreads();
-            if (tid == 0) st_release_u32(p.sched + BR_SCHED_HEADER + chain, chunk + 1);
+            if (tid == 0) {
+                const unsigned slot = p.chains + atomicAdd(p.sched + 1, 1u);   // appended entries follow the initial ones
+                st_release_u32(p.sched + BR_SCHED_HEADER + slot, 1u + chain + p.chains * (chunk + 1));
+            }
         } else {
             for (int e = tid; e < ACC_WORDS; e += Cfg::THREADS) {
                 const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);

@@ -31,6 +31,7 @@ class Engine:
         stream_ptr = ctypes.c_void_p(stream.cuda_stream if stream is not None else 0)
         rc = self.lib.nb_ctx_create(self.device.index, stream_ptr, ctypes.byref(handle))
         self.handle = handle
+        self._stream_ptr = stream_ptr.value or 0
         if rc != _native.NB_OK:
             try:
                 _native.check(handle, rc, 'nb_ctx_create')
@@ -48,7 +49,18 @@ class Engine:
 
     # --- plumbing -------------------------------------------------------------------------
     def _call(self, name, *args):
+        # work goes to torch's current stream on the engine's device unless the engine was given its own stream: that
+        # is what keeps the native launches ordered with torch's copies / fills and lets torch.cuda.graph capture them
+        if self.torch_stream is None:
+            cur = torch.cuda.current_stream(self.device).cuda_stream
+            if cur != self._stream_ptr:
+                _native.check(self.handle, self.lib.nb_ctx_set_stream(self.handle, ctypes.c_void_p(cur)), 'nb_ctx_set_stream')
+                self._stream_ptr = cur
         _native.check(self.handle, getattr(self.lib, name)(self.handle, *args), name)
+
+    def reserve(self, batch):
+        """Pre-allocate the native scratch for launches of up to `batch` ciphertexts (needed before graph capture)."""
+        self._call('nb_ctx_reserve', int(batch))
 
     def synchronize(self):
         self._call('nb_ctx_synchronize')

@@ -139,7 +139,11 @@ def gate_constant(thr, cloud_key, result: LweSampleArray, vals, perf_params=None
     # the same rule as for ciphertext arguments (gates.py:371: check_shape(result, vals)): size-1 axes broadcast
     _check_broadcast(result_shape(tuple(vals.shape)), result.shape, "the values")
     mus = numpy.where(vals.astype(bool), MU, -MU).astype(numpy.int32)
-    lwe_noiseless_trivial(thr, result, thr.to_device(numpy.ascontiguousarray(mus)))
+    if mus.ndim == 0:
+        # one bit for the whole array (gates.py:384-385): a fill, no host -> device copy (safe under graph capture)
+        lwe_noiseless_trivial_constant(thr, result, int(mus))
+    else:
+        lwe_noiseless_trivial(thr, result, thr.to_device(numpy.ascontiguousarray(mus)))
 
 
 def gate_mux(thr, cloud_key, result: LweSampleArray, a: LweSampleArray, b: LweSampleArray,

@@ -201,6 +201,63 @@ def test_uint_min_circuit(ctx, key_pair):
     assert (got == numpy.minimum(xs, ys)).all()
 
 
+def test_uint_min_as_one_cuda_graph(ctx, key_pair):
+    """The same circuit (8 x (XNOR + MUX) + MUX = 17 gates, ~60 launches / copies / fills) recorded once with
+    VirtualMachine.capture and replayed as ONE graph launch: bit-identical to the eager run, and again after the
+    operands have been refilled in place; replay is not slower than eager issue."""
+    import time
+    from nufhe_b200.operators_integer import uint_min, uintarray_to_bitarray, bitarray_to_uintarray
+    sk, ck = key_pair
+    vm = ctx.make_virtual_machine(ck)
+    rng = numpy.random.RandomState(9)
+    count = 40
+
+    def operands():
+        xs, ys = rng.randint(0, 256, count).astype(numpy.uint8), rng.randint(0, 256, count).astype(numpy.uint8)
+        return xs, ys, ctx.encrypt(sk, uintarray_to_bitarray(xs)), ctx.encrypt(sk, uintarray_to_bitarray(ys))
+    xs, ys, ca, cb = operands()
+    answer = vm.empty_ciphertext((count, 8))
+    eager = vm.empty_ciphertext((count, 8))
+    uint_min(ctx.thread, ck, eager, ca, cb, perf_params=vm.perf_params)
+    g = vm.capture(lambda: uint_min(ctx.thread, ck, answer, ca, cb, perf_params=vm.perf_params), reserve_batch=2 * count)
+    answer.a.zero_()
+    g.replay()
+    assert torch.equal(answer.a, eager.a) and torch.equal(answer.b, eager.b)
+    assert (bitarray_to_uintarray(ctx.decrypt(sk, answer)) == numpy.minimum(xs, ys)).all()
+    xs2, ys2, ca2, cb2 = operands()                       # new data into the captured operands, replay
+    for dst, src in ((ca, ca2), (cb, cb2)):
+        dst.a.copy_(src.a); dst.b.copy_(src.b); dst.current_variances.copy_(src.current_variances)
+    g.replay()
+    assert (bitarray_to_uintarray(ctx.decrypt(sk, answer)) == numpy.minimum(xs2, ys2)).all()
+    uint_min(ctx.thread, ck, eager, ca, cb, perf_params=vm.perf_params)
+    assert torch.equal(answer.a, eager.a) and torch.equal(answer.b, eager.b)
+
+    def wall(fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t
+    t_graph = min(wall(g.replay) for _ in range(3))
+    t_eager = min(wall(lambda: uint_min(ctx.thread, ck, eager, ca, cb, perf_params=vm.perf_params)) for _ in range(3))
+    print('uint_min x%d: graph %.2f ms, eager %.2f ms' % (count, 1e3 * t_graph, 1e3 * t_eager))
+    assert t_graph < 1.05 * t_eager
+
+
+def test_engine_leaves_the_callers_device_alone(nufhe):
+    """Every C entry point restores the caller's current device (one process may hold one engine per GPU).  With a
+    single GPU the guard is a no-op; with two, an engine on cuda:1 must not move torch's current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from nufhe_b200.engine import Engine
+    torch.cuda.set_device(0)
+    eng1 = Engine(1)
+    x = torch.zeros((4, 1024), dtype=torch.int32, device='cuda:1')
+    eng1.ntt_forward_i32(x)
+    assert torch.cuda.current_device() == 0
+    assert torch.empty(1, device='cuda').device.index == 0
+
+
 def test_multi_kernel_bootstrap_equals_fused(ctx, key_pair, nufhe):
     """`single_kernel_bootstrap=False` runs the reference's literal sequence of separate launches
     (bootstrap.py:96-229, gates.py:108-121, :629-664); the ciphertexts must equal the fused kernel's bit for bit."""
