@@ -53,6 +53,58 @@ NB_HD bool canon_needed(u32 hmax)
 }
 NB_HD u32 umax32(u32 a, u32 b) { return a > b ? a : b; }
 
+// EXPERIMENT, off by default (profiles/r2_variants.md): butterfly networks with deferred canonicalisation of their SUMS
+// (ff_add_nc, ntt_lane.cuh).  The network runs with the cheap additions and collects the high limbs of the sums; if one
+// of them is 2^32 - 1 (probability 2^-33 per addition) the thread restores its inputs (`reload`) and runs the exact
+// network.  165 fewer instructions per thread-step, bit-exact (GPU suite green with it) -- and 4.4 % SLOWER (86.5 against
+// 82.9 ms per 4096 bootstraps; transforms 1.71 / 1.45 against 1.96 / 1.93 TB/s): ptxas turns the carry of the new
+// sequence into SEL + LOP3 on the ALU pipe where ff_sub gets IMAD.X + IMAD.MOV on the FMA pipe (+126 ALU-pipe
+// instructions), and every network gains a divergence-barrier pair around its rare branch.
+#ifndef NB_LAZY_ADD
+#define NB_LAZY_ADD 0
+#endif
+#if defined(__CUDA_ARCH__)
+#define NB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define NB_UNLIKELY(x) (x)
+#endif
+struct NetDif16 {
+    template <bool NC> NB_HD static void run(u64 *v, u32 &h) { if constexpr (NC) dif_inlane_nc<4, 12, 0>(v, h); else dif_inlane<4, 12, 0>(v); }
+};
+struct NetDit16 {
+    template <bool NC> NB_HD static void run(u64 *v, u32 &h) { if constexpr (NC) dit_inlane_nc<4, 12, 0>(v, h); else dit_inlane<4, 12, 0>(v); }
+};
+struct NetDif4x4 {       // four 4-point transforms over a (stride 4), root 2^48
+    template <bool NC> NB_HD static void run(u64 *v, u32 &h)
+    {
+        static_for<0, 4>([&](auto E) {
+            if constexpr (NC) dif_inlane_nc<2, 48, decltype(E)::value, 4>(v, h); else dif_inlane<2, 48, decltype(E)::value, 4>(v);
+        });
+    }
+};
+struct NetDit4x4 {
+    template <bool NC> NB_HD static void run(u64 *v, u32 &h)
+    {
+        static_for<0, 4>([&](auto E) {
+            if constexpr (NC) dit_inlane_nc<2, 48, decltype(E)::value, 4>(v, h); else dit_inlane<2, 48, decltype(E)::value, 4>(v);
+        });
+    }
+};
+template <class Net, class Reload> NB_HD void run_network(u64 *v, Reload reload)
+{
+    u32 hmax = 0;
+#if NB_LAZY_ADD
+    Net::template run<true>(v, hmax);
+    if (NB_UNLIKELY(canon_needed(hmax))) {
+        reload();
+        Net::template run<false>(v, hmax);
+    }
+#else
+    (void)reload;
+    Net::template run<false>(v, hmax);
+#endif
+}
+
 constexpr int ROW_STRIDE = 66;                    // u64 per row (64 + 2 padding)
 constexpr int POLY_STRIDE = 16 * ROW_STRIDE;      // u64 per work polynomial
 
@@ -222,13 +274,16 @@ NB_HD void phase_fwd1(int task, const i32 *acc_all, u64 *w_all, const u64 *twd, 
     const int ar = a & (NTT_N - 1);
     const bool flip = (a >> 10) & 1;
     u64 v[16];
-    static_for<0, 16>([&](auto J) {
-        constexpr int j1 = decltype(J)::value;
-        const int idx = 64 * j1 + j2;
-        i32 c = ROTATE ? rotate_minus_one(acc, idx, ar, flip) : acc[idx];
-        v[j1] = ff_twist_small<j1>(decomp_udigit(c, j));
-    });
-    dif_inlane<4, 12, 0>(v);
+    auto load = [&]() {
+        static_for<0, 16>([&](auto J) {
+            constexpr int j1 = decltype(J)::value;
+            const int idx = 64 * j1 + j2;
+            i32 c = ROTATE ? rotate_minus_one(acc, idx, ar, flip) : acc[idx];
+            v[j1] = ff_twist_small<j1>(decomp_udigit(c, j));
+        });
+    };
+    load();
+    run_network<NetDif16>(v, load);
     u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     store_twiddled(v, w, twd + j2);
 }
@@ -297,7 +352,7 @@ NB_HD void phase_fwd2(int p, int row, int g, u64 *w_all)
     u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
     u64 v[16];
     load16_ae(v, w, g);
-    static_for<0, 4>([&](auto E) { dif_inlane<2, 48, decltype(E)::value, 4>(v); });
+    run_network<NetDif4x4>(v, [&]() { load16_ae(v, w, g); });
     switch (g) {           // g is warp-uniform by construction of the task map
     case 0: fwd2_twiddle<0>(v); break;
     case 1: fwd2_twiddle<1>(v); break;
@@ -311,14 +366,17 @@ NB_HD void phase_inv2(int p, int row, int g, u64 *w_all)
 {
     u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
     u64 v[16];
-    load16_ae(v, w, g);
-    switch (g) {
-    case 0: inv2_twiddle<0>(v); break;
-    case 1: inv2_twiddle<1>(v); break;
-    case 2: inv2_twiddle<2>(v); break;
-    default: inv2_twiddle<3>(v); break;
-    }
-    static_for<0, 4>([&](auto E) { dit_inlane<2, 48, decltype(E)::value, 4>(v); });
+    auto load = [&]() {
+        load16_ae(v, w, g);
+        switch (g) {
+        case 0: inv2_twiddle<0>(v); break;
+        case 1: inv2_twiddle<1>(v); break;
+        case 2: inv2_twiddle<2>(v); break;
+        default: inv2_twiddle<3>(v); break;
+        }
+    };
+    load();
+    run_network<NetDit4x4>(v, load);
     store16_ae(v, w, g);
 }
 
@@ -328,7 +386,7 @@ NB_HD void phase_fwd3(int p, int row, int u, u64 *w_all)
     u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
     u64 v[16];
     load16_b(v, w, u);
-    dif_inlane<4, 12, 0>(v);
+    run_network<NetDif16>(v, [&]() { load16_b(v, w, u); });
     store16_b(v, w, u);
 }
 NB_HD void phase_inv3(int p, int row, int u, u64 *w_all)
@@ -336,7 +394,7 @@ NB_HD void phase_inv3(int p, int row, int u, u64 *w_all)
     u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
     u64 v[16];
     load16_b(v, w, u);
-    dit_inlane<4, 12, 0>(v);
+    run_network<NetDit16>(v, [&]() { load16_b(v, w, u); });
     store16_b(v, w, u);
 }
 
@@ -418,7 +476,7 @@ NB_HD void phase_inv1(int task, i32 *acc_all, const u64 *w_all, const u64 *twd_i
     const u64 *w = w_all + (ct * 4 + mo) * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     u64 v[16];
     load_twiddled(v, w, twd_inv + j2);
-    dit_inlane<4, 12, 0>(v);
+    run_network<NetDit16>(v, [&]() { load_twiddled(v, w, twd_inv + j2); });
     i32 *acc = acc_all + (ct * 2 + mo) * NTT_N;
     static_for<0, 16>([&](auto J) {
         constexpr int j1 = decltype(J)::value;
@@ -455,7 +513,7 @@ NB_HD void phase_fwd1_generic(int task, const u64 *x /* 16 values, x[j1] = in[64
         constexpr int j1 = decltype(J)::value;
         v[j1] = ff_shl<6 * j1>(x[j1]);
     });
-    dif_inlane<4, 12, 0>(v);
+    run_network<NetDif16>(v, [&]() { static_for<0, 16>([&](auto J) { constexpr int j1 = decltype(J)::value; v[j1] = ff_shl<6 * j1>(x[j1]); }); });
     u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     store_twiddled(v, w, twd + j2);
 }
@@ -468,7 +526,7 @@ NB_HD void phase_fwd1_i32(int task, const i32 *x /* 16 values, x[j1] = in[64 j1 
         constexpr int j1 = decltype(J)::value;
         v[j1] = ff_twist_i32<j1>(x[j1]);
     });
-    dif_inlane<4, 12, 0>(v);
+    run_network<NetDif16>(v, [&]() { static_for<0, 16>([&](auto J) { constexpr int j1 = decltype(J)::value; v[j1] = ff_twist_i32<j1>(x[j1]); }); });
     u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     store_twiddled(v, w, twd + j2);
 }
@@ -479,7 +537,7 @@ NB_HD void phase_inv1_generic(int task, u64 *y, const u64 *w_all, const u64 *twd
     const u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     u64 v[16];
     load_twiddled(v, w, twd_inv + j2);
-    dit_inlane<4, 12, 0>(v);
+    run_network<NetDit16>(v, [&]() { load_twiddled(v, w, twd_inv + j2); });
     static_for<0, 16>([&](auto J) {
         constexpr int j1 = decltype(J)::value;
         y[j1] = ff_shl<(192 - 6 * j1) % 192>(v[j1]);
@@ -494,7 +552,7 @@ NB_HD void phase_inv1_i32(int task, i32 *y, const u64 *w_all, const u64 *twd_inv
     const u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     u64 v[16];
     load_twiddled(v, w, twd_inv + j2);
-    dit_inlane<4, 12, 0>(v);
+    run_network<NetDit16>(v, [&]() { load_twiddled(v, w, twd_inv + j2); });
     y[0] = ff_to_i32(v[0]);
     static_for<1, 16>([&](auto J) {
         constexpr int j1 = decltype(J)::value;

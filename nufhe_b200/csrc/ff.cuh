@@ -107,6 +107,30 @@ NB_HD u64 ff_add(u64 a, u64 b)
 #endif
 }
 
+// a + b for a, b in [0, p] as "some 64-bit value of the right residue": the 64-bit sum, minus p (= plus eps mod 2^64)
+// when it wrapped -- no second wrap is possible (a + b - 2^64 + eps <= p).  A sum that did NOT wrap is left alone; it
+// lies above p only if it falls into (p, 2^64), probability 2^-33 for uniform operands, and then its high limb is
+// 2^32 - 1.  The butterfly networks that use this form watch the high limbs and redo their task with ff_add when one
+// shows up (ntt_lane.cuh, br_phases.cuh); one ALU instruction per addition saved against ff_add = ff_sub(a, p - b).
+NB_HD u64 ff_add_nc(u64 a, u64 b)
+{
+#if defined(__CUDA_ARCH__)
+    u32 l, h, g, ng;
+    asm("add.cc.u32 %0, %4, %6;\n\t"
+        "addc.cc.u32 %1, %5, %7;\n\t"
+        "addc.u32 %2, 0, 0;\n\t"           // g = carry out of the 64-bit sum
+        "sub.u32 %3, 0, %2;\n\t"           // -g
+        "sub.cc.u32 %0, %0, %2;\n\t"       // + g * eps = - g + g * 2^32: low limb, borrow iff it was 0
+        "subc.u32 %1, %1, %3;"             // high limb + g - borrow
+        : "=&r"(l), "=&r"(h), "=&r"(g), "=&r"(ng)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+    (void)ng;
+    return pack(l, h);
+#else
+    return ff_add(a, b);
+#endif
+}
+
 // v * (2^32 - 1) for a 32-bit v: always canonical ((2^32-1)^2 < p).
 NB_HD u64 ff_eps_mul(u32 v)
 {

@@ -45,6 +45,26 @@ template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dif_inlane
     });
 }
 
+// The same network with additions in the ff_add_nc form; hmax collects the high limbs of the sums (see ff_add_nc)
+NB_HD u32 nb_umax(u32 a, u32 b) { return a > b ? a : b; }
+template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dif_inlane_nc(u64 *v, u32 &hmax)
+{
+    constexpr int n = 1 << LOGN;
+    static_for<0, LOGN>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        constexpr int half = n >> (s + 1);
+        static_for<0, n / 2>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            constexpr int blk = q / half, k = q % half;
+            constexpr int i0 = BASE + (blk * 2 * half + k) * STRIDE, i1 = i0 + half * STRIDE;
+            u64 a = v[i0], b = v[i1];
+            v[i0] = ff_add_nc(a, b);
+            hmax = nb_umax(hmax, hi32(v[i0]));
+            v[i1] = ff_shl<(ROOTLOG * k * (1 << s)) % 192>(ff_sub(a, b));
+        });
+    });
+}
+
 // The exact inverse network (up to the factor 2^LOGN): decimation in time with the inverse root.
 template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dit_inlane(u64 *v)
 {
@@ -66,6 +86,32 @@ template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dit_inlane
             } else {
                 u64 a = v[i0], t = ff_shl<(192 - e) % 192>(v[i1]);
                 v[i0] = ff_add(a, t);
+                v[i1] = ff_sub(a, t);
+            }
+        });
+    });
+}
+
+template <int LOGN, int ROOTLOG, int BASE, int STRIDE = 1> NB_HD void dit_inlane_nc(u64 *v, u32 &hmax)
+{
+    constexpr int n = 1 << LOGN;
+    static_for<0, LOGN>([&](auto S) {
+        constexpr int s = LOGN - 1 - decltype(S)::value;
+        constexpr int half = n >> (s + 1);
+        static_for<0, n / 2>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            constexpr int blk = q / half, k = q % half;
+            constexpr int i0 = BASE + (blk * 2 * half + k) * STRIDE, i1 = i0 + half * STRIDE;
+            constexpr int e = (ROOTLOG * k * (1 << s)) % 192;
+            if constexpr (e > 0 && e < 96) {
+                u64 a = v[i0], t = ff_shl<96 - e>(v[i1]);
+                v[i0] = ff_sub(a, t);
+                v[i1] = ff_add_nc(a, t);
+                hmax = nb_umax(hmax, hi32(v[i1]));
+            } else {
+                u64 a = v[i0], t = ff_shl<(192 - e) % 192>(v[i1]);
+                v[i0] = ff_add_nc(a, t);
+                hmax = nb_umax(hmax, hi32(v[i0]));
                 v[i1] = ff_sub(a, t);
             }
         });

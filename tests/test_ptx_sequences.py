@@ -54,6 +54,11 @@ def ff_add(a, b):
     return ff_sub(a, (P - b) & M64)
 
 
+def ff_add_nc(a, b):
+    e = run('ff_add_nc', a=a, b=b)
+    return HELPERS['pack'](e['l'], e['h'])
+
+
 def ff_add_keps(v0, v1, k):
     e = run('ff_add_keps', v0=v0, v1=v1, k=k)
     return HELPERS['pack'](e['v0'], (e['v1'] + k) & M32)
@@ -184,6 +189,20 @@ def test_sub_add_all_edge_pairs():
     for a, b in zip(rand_field(2000), rand_field(2000)):
         assert ff_sub(a, b) % P == (a - b) % P and in_range(ff_sub(a, b))
         assert ff_add(a, b) % P == (a + b) % P and in_range(ff_add(a, b))
+
+
+def test_add_nc_all_edge_pairs():
+    """ff_add_nc: the sum as any 64-bit value of the right residue; above p only without a wrap, and then its high
+    limb is 2^32 - 1 (what the butterfly networks' trigger watches)."""
+    assert len(blocks('ff_add_nc')) == 1
+    pairs = [(a, b) for a in EDGE64 for b in EDGE64] + list(zip(rand_field(3000), rand_field(3000)))
+    for a, b in pairs:
+        got = ff_add_nc(a, b)
+        assert 0 <= got < 1 << 64 and got % P == (a + b) % P, (hex(a), hex(b), hex(got))
+        if got > P:
+            assert a + b < 1 << 64 and got >> 32 == M32, (hex(a), hex(b), hex(got))
+    # the window (p, 2^64) is reachable: p - 1 + 5 does not wrap and is left alone
+    assert ff_add_nc(P - 1, 5) == P + 4
 
 
 def test_canon_and_keps():

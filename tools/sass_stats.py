@@ -118,7 +118,7 @@ def main():
     rare_lines = set()
     bsrc = open(bpath).read().splitlines()
     for i, l in enumerate(bsrc, 1):
-        if 'if (canon_needed(' in l:
+        if 'canon_needed(' in l and l.lstrip().startswith('if '):
             depth, j = 0, i
             while True:
                 depth += bsrc[j - 1].count('{') - bsrc[j - 1].count('}')
