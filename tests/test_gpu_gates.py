@@ -227,6 +227,22 @@ def test_time_sliced_launches_equal_the_oracle(eng, keys, dev_keys, batch):
     assert (out[0] == want[0]).all() and (out[1] == want[1]).all()
 
 
+def test_time_sliced_mux_equals_the_oracle(eng, keys, dev_keys):
+    """gate_mux's double launch (two jobs in one kernel, nb_bootstrap_extract2) through the time-sliced queue: 2 x 330
+    ciphertexts = 330 chains on 296 CTAs; and one batch in the time-sliced WIDE shape (2 x 200 ciphertexts)."""
+    bk_int, ks = dev_keys
+    and_const = O.phase_to_t32(-1, 8)
+    for B in (330, 200):
+        rng = G.rs(3300 + B)
+        bits = [rng.randint(0, 2, B).astype(bool) for _ in range(3)]
+        a, b, c = (keys.encrypt(x) for x in bits)
+        d = [(eng.to_device(x[0]), eng.to_device(x[1])) for x in (a, b, c)]
+        u1, u2 = eng.bootstrap_extract2((d[0], d[1], and_const, 1, 1), (d[0], d[2], and_const, -1, 1), O.MU, bk_int)
+        ma, mb, _ = eng.keyswitch(ks, u1, u2, c=O.phase_to_t32(1, 8))
+        want = O.gate_mux(a, b, c, keys.bk, keys.ks)
+        assert (eng.to_host(ma) == want[0]).all() and (eng.to_host(mb) == want[1]).all(), B
+
+
 _RARE_PATH_SCRIPT = r'''
 import sys, numpy
 sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/tests/golden')
