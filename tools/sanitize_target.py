@@ -26,5 +26,21 @@ big = (r32((300, 1024)), r32((300,)))
 eng.keyswitch(ks, big, big, c=5)
 p = r32((9, 1024))
 eng.ntt_inverse_i32(eng.ntt_forward_i32(p))
+# round 2: the work queue (more chains than resident CTAs, forced into 3 chunks with NUFHE_B200_FORCE_CHUNKS=3 so that
+# accumulators are parked and resumed even with n = 3 steps), both CTA shapes; u64 transforms through the staging
+# buffers (several sweeps per CTA); the LWE dot product and the key-switch-key kernel
+B = int(os.environ.get('SANITIZE_BATCH', '700'))
+xa, xb = (r32((B, n)), r32((B,))), (r32((B, n)), r32((B,)))
+eng.bootstrap_extract(xa, xb, 2**29, -1, -1, 2**29, bk)
+eng.bootstrap_extract2((xa, xb, 5, 1, 1), (xa, xb, 7, -1, 1), 2**29, bk)
+pu = rff((2500, 1024))
+eng.ntt_inverse_u64(eng.ntt_forward_u64(pu))
+eng.ntt_inverse_i32(eng.ntt_forward_i32(r32((2500, 1024))))
+key = r32((500,), 0, 2)
+eng.lwe_dot(r32((77, 500)), key, add1=r32((77,)), add2=r32((77,)), sign=-1)
+ks_a = torch.empty((16, 8, 4, 500), dtype=torch.int32).cuda()
+ks_b = torch.empty((16, 8, 4), dtype=torch.int32).cuda()
+ks_cv = torch.empty((16, 8, 4), dtype=torch.float32).cuda()
+eng.make_keyswitch_key(ks_a, ks_b, ks_cv, r32((16,), 0, 2), key, r32((16, 8, 3, 500)), r32((16, 8, 3)), 2, 1e-9)
 torch.cuda.synchronize()
 print('sanitize target done')
