@@ -112,9 +112,9 @@ def tlwe_encrypt_zero(thr, rng, result: TLweSampleArray, noise: float, key: TLwe
     tr_noise = thr.ntt_forward_i32(noises1)                          # shape + (k, N)
     prod = thr.ff_op(_native.FF_MUL, tr_noise, tr_key)               # key broadcast with period k*N
     conv = thr.ntt_inverse_i32(prod)                                 # shape + (k, N)
-    body = noises2.to(torch.int64) + conv.to(torch.int64).sum(-2)
-    body = body & 0xffffffff
-    body = torch.where(body >= 2**31, body - 2**32, body).to(torch.int32)
+    body = noises2.contiguous()                                      # Torus32 wrap-around sums on the engine (nb_tlwe_add_to)
+    for i in range(k):
+        thr.tlwe_add_to(body, conv[..., i, :].contiguous())
     result.a.coeffs[..., :k, :] = noises1
     result.a.coeffs[..., k, :] = body
     result.current_variances.fill_(float(numpy.float32(noise**2)))
