@@ -91,19 +91,28 @@ def lib_sha():
         return hashlib.sha256(f.read()).hexdigest()[:16]
 
 
-def measured_traffic(batch):
+def measured_traffic(batch, counts=None):
     """dram__bytes_read + dram__bytes_write of one blind-rotate launch from the committed ncu capture of this round
-    (profiles/r2_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` run; a profiler cannot run
-    inside the bench).  Returns (bytes or None, provenance)."""
+    (profiles/r2_traffic.json, written by tools/ncu_traffic.py from an ncu run of tools/profile_target.py; a profiler
+    cannot run inside the bench).  The capture carries the hash of the library it was taken on and the static SASS
+    instruction counts of its step loop; the provenance says whether the library of THIS run is the same file, or at
+    least the same kernel code (same per-phase counts -- e.g. rebuilt after a comment changed the line info).
+    Returns (bytes or None, provenance)."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as f:
             d = json.load(f)
         if int(d['batch']) != int(batch):
             return None, 'profiles/r2_traffic.json was captured at batch %s' % d['batch']
         k = d['blind_rotate_kernel']
-        same = d.get('lib_sha') == lib_sha()
+        fp = d.get('kernel_fingerprint')
+        if d.get('lib_sha') == lib_sha():
+            which = 'this build'
+        elif counts and fp and fp.get('phases') == counts.get('phases'):
+            which = 'same kernel code as this build: identical static instruction counts per phase'
+        else:
+            which = 'an earlier r2 build'
         return (int(k['dram_bytes_read']) + int(k['dram_bytes_write']),
-                'ncu capture profiles/r2_traffic.json (%s build)' % ('this' if same else 'an earlier r2'))
+                'ncu capture profiles/r2_traffic.json (%s)' % which)
     except Exception as e:
         return None, 'no capture (%s)' % type(e).__name__
 
@@ -447,7 +456,8 @@ def run_b200_arm(args):
         n_ops = main['n_ops']
         h2d = world * n_ops * (B * LWE_N * 4 + B * 4)     # whole job, all ranks
         d2h = world * (B * LWE_N * 4 + B * 4)
-        traffic, traffic_src = measured_traffic(B)
+        counts = static_instruction_counts()
+        traffic, traffic_src = measured_traffic(B, counts)
         line = {
             'metric': metric_name(args), 'value': value, 'unit': 'gates/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
@@ -476,7 +486,6 @@ def run_b200_arm(args):
                                'ok': parity_ok, 'against': 'CPU oracle (oracle/), same seeded keys'},
             'build': thr.build_info(), 'lib_sha': lib_sha(),
         }
-        counts = static_instruction_counts()
         if counts:
             per_thread = counts['per_thread_step_total']
             warp_instr = per_thread * LWE_N * B * THREADS_PER_CT / 32.0

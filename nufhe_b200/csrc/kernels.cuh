@@ -2,9 +2,11 @@
 //
 // Work decomposition of the fused bootstrap: a CTA owns one or two ciphertexts whose accumulators and work
 // polynomials live in shared memory; every CMux step is seven CTA-wide phases (br_phases.cuh) separated by
-// __syncthreads, 16 field elements per thread and phase.  The stand-alone transforms reuse the same phases.
-// The key switch is a TMA-fed producer / consumer pipeline.  The small kernels at the end are the separate steps of
-// the reference's multi-kernel bootstrap.
+// __syncthreads, 16 field elements per thread and phase.  The kernel is persistent: at most one wave of CTAs, which
+// pull (chain, chunk) work items from a FIFO of ready chains in global memory, so that any batch is spread over all SMs.
+// The stand-alone transforms reuse the same phases behind cp.async-staged, 128-bit input / output.  The key switch is a
+// TMA-fed producer / consumer pipeline.  Then the separate steps of the reference's multi-kernel bootstrap, and the
+// key-generation kernels (LWE dot product, key-switch key).
 //
 // Reference counterparts: nufhe/blind_rotate.mako:18-226 (fused bootstrap), tgsw_gpu.py:110-169
 // (external product), transform/computation.mako:18-143 (stand-alone transform), lwe_gpu.mako:59-118

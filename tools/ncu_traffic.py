@@ -27,6 +27,13 @@ for r in rows:
     v *= {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
     res.setdefault(key, {})['dram_bytes_read' if 'read' in metric else 'dram_bytes_write'] = int(v)   # last launch wins
 lib = os.environ.get('NUFHE_B200_LIB') or os.path.join(ROOT, 'nufhe_b200', 'csrc', 'libnufhe_b200.so')
+try:
+    import subprocess
+    st = json.loads(subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'sass_stats.py'), '--json', '--lib', lib],
+                                   capture_output=True, text=True, timeout=300).stdout.strip().splitlines()[-1])
+    res['kernel_fingerprint'] = {'per_thread_step_total': st['per_thread_step_total'], 'phases': st['phases']}
+except Exception:
+    pass
 res.update({'source': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, tools/profile_target.py %d (%s)' % (batch, os.path.basename(src)),
             'batch': batch, 'lib_sha': hashlib.sha256(open(lib, 'rb').read()).hexdigest()[:16]})
 json.dump(res, open(out, 'w'), indent=1)
