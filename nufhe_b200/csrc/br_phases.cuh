@@ -120,6 +120,9 @@ template <int CT_, int THREADS_, int CTAS_ = 512 / THREADS_, bool TWD_GLOBAL_ = 
     static constexpr int POLYS = 4 * CT;                       // work polynomials per CTA
     static constexpr int FWD_SWEEPS = 256 * CT / THREADS;      // sweeps of the forward phases
     static constexpr int INV_TASKS = 128 * CT;                 // threads with work in the inverse phases
+    // Twice as many threads as inverse tasks (the wide shape): every inverse task is shared by two threads of
+    // different warps, 8 elements each ("split inverse phases" below) instead of leaving half of the warps idle
+    static constexpr bool SPLIT_INV = 2 * INV_TASKS <= THREADS;
     static constexpr int CTAS_PER_SM = CTAS_;                  // default 512 / THREADS: 16 warps per SM at 128 registers
     static constexpr bool TWD_GLOBAL = TWD_GLOBAL_;            // twiddle tables read from global memory / L1, not staged
     static_assert(FWD_SWEEPS >= 1 && FWD_SWEEPS * THREADS == 256 * CT && INV_TASKS <= THREADS && THREADS % 128 == 0, "shape");
@@ -398,6 +401,149 @@ NB_HD void phase_inv3(int p, int row, int u, u64 *w_all)
     store16_b(v, w, u);
 }
 
+// ---- split inverse phases (Cfg::SPLIT_INV) --------------------------------------------------------------------------
+// A 16-point decimation-in-time network is two 8-point networks on elements 0-7 and 8-15 (the first three layers:
+// dit_inlane<3, 24>) followed by one layer that pairs element k with element 8 + k.  Thread half h = 0 / 1 (a whole
+// warp either way) runs the 8-point network on its elements, half 1 also applies the last layer's twiddles, and both
+// park their 8 values in the work polynomial p + 2 -- dead since the MAC, which overwrote polynomials 0 and 1 of the
+// ciphertext with its outputs -- at the positions they were read from.  After a CTA barrier each thread reads the 16
+// parked values of its task and finishes ITS 8 outputs.  The per-thread instruction stream of the inverse phases
+// halves, which is what the latency of a step is made of when few warps are resident.
+template <int H> NB_HD void dit16_half_a(u64 *v8)
+{
+    dit_inlane<3, 24, 0>(v8);
+    if constexpr (H == 1) {
+        // last-layer twiddles 2^(-12 k) = -2^(96 - 12 k), k >= 1: shift by the positive amount, the sign goes into
+        // the add / sub choice of dit16_half_b (as in dit_inlane)
+        static_for<1, 8>([&](auto K) { constexpr int k = decltype(K)::value; v8[k] = ff_shl<96 - 12 * k>(v8[k]); });
+    }
+}
+// a[k], t[k]: the parked values of elements k and 8 + k; o[k]: output element 8 H + k
+template <int H> NB_HD void dit16_half_b(const u64 *a, const u64 *t, u64 *o)
+{
+    static_for<0, 8>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        constexpr bool sub = (H == 1) != (k >= 1);       // element k: a + t for k = 0, a - t otherwise; element 8 + k: the reverse
+        o[k] = sub ? ff_sub(a[k], t[k]) : ff_add(a[k], t[k]);
+    });
+}
+
+// inv3, first half: task (p, row, u), elements 8 H .. 8 H + 7 of block u (logical pairs 4 H .. 4 H + 3)
+template <int H> NB_HD void phase_inv3_split_a(int p, int row, int u, u64 *w_all)
+{
+    const u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    u64 *x = w_all + (p + 2) * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[8];
+    static_for<0, 4>([&](auto PI) {
+        constexpr int pi = 4 * H + decltype(PI)::value;
+        ld2(w + 16 * u + 2 * ((pi ^ (2 * u)) & 7), v[2 * decltype(PI)::value], v[2 * decltype(PI)::value + 1]);
+    });
+    dit16_half_a<H>(v);
+    static_for<0, 4>([&](auto PI) {
+        constexpr int pi = 4 * H + decltype(PI)::value;
+        st2(x + 16 * u + 2 * ((pi ^ (2 * u)) & 7), v[2 * decltype(PI)::value], v[2 * decltype(PI)::value + 1]);
+    });
+}
+template <int H> NB_HD void phase_inv3_split_b(int p, int row, int u, u64 *w_all)
+{
+    u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    const u64 *x = w_all + (p + 2) * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[16], o[8];
+    load16_b(v, x, u);
+    dit16_half_b<H>(v, v + 8, o);
+    static_for<0, 4>([&](auto PI) {
+        constexpr int pi = 4 * H + decltype(PI)::value;
+        st2(w + 16 * u + 2 * ((pi ^ (2 * u)) & 7), o[2 * decltype(PI)::value], o[2 * decltype(PI)::value + 1]);
+    });
+}
+
+// inv2: the four 4-point transforms of a task are independent; half H takes e = 2 H, 2 H + 1 (no exchange)
+template <int G, int H> NB_HD void inv2_twiddle_half(u64 *v8)        // v8[a * 2 + e'], e = 2 H + e'
+{
+    static_for<1, 4>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        constexpr int kappa = brev(u, 2);
+        static_for<0, 2>([&](auto E) {
+            constexpr int e = 2 * H + decltype(E)::value;
+            v8[u * 2 + decltype(E)::value] = ff_shl<(192 - (3 * kappa * (4 * G + e)) % 192) % 192>(v8[u * 2 + decltype(E)::value]);
+        });
+    });
+}
+template <int H> NB_HD void phase_inv2_split(int p, int row, int g, u64 *w_all)
+{
+    u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[8];
+    static_for<0, 4>([&](auto A) {
+        constexpr int a = decltype(A)::value;
+        ld2(w + 16 * a + 4 * (g ^ a) + 2 * H, v[a * 2], v[a * 2 + 1]);
+    });
+    switch (g) {           // warp-uniform, like phase_inv2
+    case 0: inv2_twiddle_half<0, H>(v); break;
+    case 1: inv2_twiddle_half<1, H>(v); break;
+    case 2: inv2_twiddle_half<2, H>(v); break;
+    default: inv2_twiddle_half<3, H>(v); break;
+    }
+    static_for<0, 2>([&](auto E) { dit_inlane<2, 48, decltype(E)::value, 2>(v); });
+    static_for<0, 4>([&](auto A) {
+        constexpr int a = decltype(A)::value;
+        st2(w + 16 * a + 4 * (g ^ a) + 2 * H, v[a * 2], v[a * 2 + 1]);
+    });
+}
+
+// inv1, first half: task = (ct, mo, j2); rows 8 H .. 8 H + 7 of column j2, times the twiddles, 8-point network
+template <int H> NB_HD void phase_inv1_split_a(int task, u64 *w_all, const u64 *twd_inv)
+{
+    const int j2 = task & 63, pp = task >> 6;
+    const int p = (pp >> 1) * 4 + (pp & 1);
+    const int col = col_of(j2 >> 4, j2 & 15);
+    const u64 *w = w_all + p * POLY_STRIDE + col + 8 * H * ROW_STRIDE;
+    u64 *x = w_all + (p + 2) * POLY_STRIDE + col + 8 * H * ROW_STRIDE;
+    const u64 *twd = twd_inv + 8 * H * 64 + j2;
+    u64 v[8];
+    u32 hmax = 0;
+    static_for<0, 8>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+#if NB_LAZY_CANON
+        v[r] = ff_mul_nc(w[r * ROW_STRIDE], twd[r * 64]);
+        hmax = umax32(hmax, hi32(v[r]));
+#else
+        v[r] = ff_mul(w[r * ROW_STRIDE], twd[r * 64]);
+#endif
+    });
+#if NB_LAZY_CANON
+    if (canon_needed(hmax)) {
+        static_for<0, 8>([&](auto R) { v[decltype(R)::value] = ff_canon_almost(v[decltype(R)::value]); });
+    }
+#endif
+    dit16_half_a<H>(v);
+    static_for<0, 8>([&](auto R) { x[decltype(R)::value * ROW_STRIDE] = v[decltype(R)::value]; });
+}
+template <bool ACCUMULATE, int H> NB_HD void phase_inv1_split_b(int task, i32 *acc_all, const u64 *w_all)
+{
+    const int j2 = task & 63, pp = task >> 6;
+    const int ct = pp >> 1, mo = pp & 1;
+    const u64 *x = w_all + (ct * 4 + mo + 2) * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
+    u64 a[8], t[8], o[8];
+    static_for<0, 8>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        a[k] = x[k * ROW_STRIDE];
+        t[k] = x[(8 + k) * ROW_STRIDE];
+    });
+    dit16_half_b<H>(a, t, o);
+    i32 *acc = acc_all + (ct * 2 + mo) * NTT_N;
+    static_for<0, 8>([&](auto K) {
+        constexpr int j1 = 8 * H + decltype(K)::value;
+        const int idx = 64 * j1 + j2;
+        if constexpr (j1 == 0) {
+            i32 r = ff_to_i32(o[0]);
+            acc[idx] = ACCUMULATE ? (i32)((u32)acc[idx] + (u32)r) : r;
+        } else {
+            u32 r = (u32)ff_to_i32(ff_shl<96 - 6 * j1>(o[decltype(K)::value]));
+            acc[idx] = ACCUMULATE ? (i32)((u32)acc[idx] - r) : (i32)(0u - r);
+        }
+    });
+}
+
 // ---- MAC: thread = (row, pair q): stored columns 2q, 2q+1 of every work polynomial -----------------
 // bk_row: internal layout [mi][j][mo][row * 64 + stored column], plain (non-Montgomery) values.
 // out polynomial mo of ciphertext ct overwrites work polynomial ct*4 + mo.
@@ -582,6 +728,18 @@ template <class Cfg = BrDefault> NB_HD bool map_inv2(int tid, int &p, int &row, 
     p = (pp >> 1) * 4 + (pp & 1);
     return x < 32 * Cfg::CT;
 }
+// split inverse phases: h = thread half (warps 0 .. THREADS/64 - 1: h = 0, the others h = 1), t = task of the unsplit map
+template <class Cfg> NB_HD void map_split(int tid, int &h, int &t) { h = tid >= Cfg::INV_TASKS; t = tid - h * Cfg::INV_TASKS; }
+// inv2 tasks of the split phases: t in [0, INV_TASKS), g warp-uniform (32 consecutive tasks per g and polynomial pair)
+template <class Cfg> NB_HD void map_inv2_split(int t, int &p, int &row, int &g)
+{
+    constexpr int Q = Cfg::INV_TASKS / 4;              // tasks per value of g: 2 CT polynomials x 16 rows
+    g = t / Q;
+    const int x = t % Q, pp = x >> 4;
+    row = x & 15;
+    p = (pp >> 1) * 4 + (pp & 1);
+}
+
 template <class Cfg = BrDefault> NB_HD bool map_inv3(int tid, int &p, int &row, int &u)
 {
     u = tid & 3; row = (tid >> 2) & 15;

@@ -116,11 +116,24 @@ template <class Cfg> static void phase_step(i32 *acc_io, const u64 *bk_ref_row, 
     for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
         for (int tid = 0; tid < TH; tid++) { int p, r, u; map_fwd3<Cfg>(tid, it, p, r, u); phase_fwd3(p, r, u, w.data()); }
     for (int tid = 0; tid < TH; tid++) phase_mac<Cfg>(tid, w.data(), bk.data());
-    for (int tid = 0; tid < TH; tid++) { int p, r, u; if (map_inv3<Cfg>(tid, p, r, u)) phase_inv3(p, r, u, w.data()); }
-    for (int tid = 0; tid < TH; tid++) { int p, r, g; if (map_inv2<Cfg>(tid, p, r, g)) phase_inv2(p, r, g, w.data()); }
-    for (int tid = 0; tid < Cfg::INV_TASKS; tid++) {
-        if (rot) phase_inv1<true>(tid, acc.data(), w.data(), T.inv.data());
-        else phase_inv1<false>(tid, acc.data(), w.data(), T.inv.data());
+    if constexpr (Cfg::SPLIT_INV) {
+        // the split inverse phases of the wide shape, one loop per barrier-separated sub-pass (kernels.cuh: br2_step)
+        auto each = [&](auto fn) { for (int tid = 0; tid < TH; tid++) { int h, t; map_split<Cfg>(tid, h, t); fn(h, t); } };
+        each([&](int h, int t) { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_a<1>(p, r, u, w.data()); else phase_inv3_split_a<0>(p, r, u, w.data()); });
+        each([&](int h, int t) { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_b<1>(p, r, u, w.data()); else phase_inv3_split_b<0>(p, r, u, w.data()); });
+        each([&](int h, int t) { int p, r, g; map_inv2_split<Cfg>(t, p, r, g); if (h) phase_inv2_split<1>(p, r, g, w.data()); else phase_inv2_split<0>(p, r, g, w.data()); });
+        each([&](int h, int t) { if (h) phase_inv1_split_a<1>(t, w.data(), T.inv.data()); else phase_inv1_split_a<0>(t, w.data(), T.inv.data()); });
+        each([&](int h, int t) {
+            if (rot) { if (h) phase_inv1_split_b<true, 1>(t, acc.data(), w.data()); else phase_inv1_split_b<true, 0>(t, acc.data(), w.data()); }
+            else { if (h) phase_inv1_split_b<false, 1>(t, acc.data(), w.data()); else phase_inv1_split_b<false, 0>(t, acc.data(), w.data()); }
+        });
+    } else {
+        for (int tid = 0; tid < TH; tid++) { int p, r, u; if (map_inv3<Cfg>(tid, p, r, u)) phase_inv3(p, r, u, w.data()); }
+        for (int tid = 0; tid < TH; tid++) { int p, r, g; if (map_inv2<Cfg>(tid, p, r, g)) phase_inv2(p, r, g, w.data()); }
+        for (int tid = 0; tid < Cfg::INV_TASKS; tid++) {
+            if (rot) phase_inv1<true>(tid, acc.data(), w.data(), T.inv.data());
+            else phase_inv1<false>(tid, acc.data(), w.data(), T.inv.data());
+        }
     }
     for (int c = 0; c < nct; c++) memcpy(acc_io + c * 2 * NTT_N, &acc[c * 2 * NTT_N], sizeof(i32) * 2 * NTT_N);
 }

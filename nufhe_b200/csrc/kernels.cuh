@@ -352,12 +352,29 @@ NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *
     // multiply-accumulate with the key row (tgsw_gpu.py:58-107); each key element is fetched once per CTA
     phase_mac<Cfg>(tid, s.w, bk_row);
     __syncthreads();
-    // inverse transforms of the output polynomials (threads beyond Cfg::INV_TASKS idle: whole warps)
-    { int p, r, u; if (map_inv3<Cfg>(tid, p, r, u)) phase_inv3(p, r, u, s.w); }
-    __syncthreads();
-    { int p, r, g; if (map_inv2<Cfg>(tid, p, r, g)) phase_inv2(p, r, g, s.w); }
-    __syncthreads();
-    if (tid < Cfg::INV_TASKS) phase_inv1<ROTATE>(tid, s.acc, s.w, s.twd_inv);
+    // inverse transforms of the output polynomials
+    if constexpr (Cfg::SPLIT_INV) {
+        // twice as many threads as tasks: two threads (of different warps) per task, 8 elements each, parked values
+        // exchanged through the dead work polynomials (br_phases.cuh: split inverse phases); two more barriers
+        int h, t;
+        map_split<Cfg>(tid, h, t);
+        { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_a<1>(p, r, u, s.w); else phase_inv3_split_a<0>(p, r, u, s.w); }
+        __syncthreads();
+        { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_b<1>(p, r, u, s.w); else phase_inv3_split_b<0>(p, r, u, s.w); }
+        __syncthreads();
+        { int p, r, g; map_inv2_split<Cfg>(t, p, r, g); if (h) phase_inv2_split<1>(p, r, g, s.w); else phase_inv2_split<0>(p, r, g, s.w); }
+        __syncthreads();
+        if (h) phase_inv1_split_a<1>(t, s.w, s.twd_inv); else phase_inv1_split_a<0>(t, s.w, s.twd_inv);
+        __syncthreads();
+        if (h) phase_inv1_split_b<ROTATE, 1>(t, s.acc, s.w); else phase_inv1_split_b<ROTATE, 0>(t, s.acc, s.w);
+    } else {
+        // (threads beyond Cfg::INV_TASKS idle: whole warps)
+        { int p, r, u; if (map_inv3<Cfg>(tid, p, r, u)) phase_inv3(p, r, u, s.w); }
+        __syncthreads();
+        { int p, r, g; if (map_inv2<Cfg>(tid, p, r, g)) phase_inv2(p, r, g, s.w); }
+        __syncthreads();
+        if (tid < Cfg::INV_TASKS) phase_inv1<ROTATE>(tid, s.acc, s.w, s.twd_inv);
+    }
 }
 
 NB_D unsigned ld_acquire_u32(const unsigned *p)
