@@ -118,14 +118,17 @@ constexpr int POLY_STRIDE = 16 * ROW_STRIDE;      // u64 per work polynomial
 template <int CT_, int THREADS_, int CTAS_ = 512 / THREADS_, bool TWD_GLOBAL_ = false> struct BrCfg {
     static constexpr int CT = CT_, THREADS = THREADS_;
     static constexpr int POLYS = 4 * CT;                       // work polynomials per CTA
-    static constexpr int FWD_SWEEPS = 256 * CT / THREADS;      // sweeps of the forward phases
+    // Twice as many threads as forward tasks ("wide2": 1 ciphertext on 512 threads): two threads of different warps per
+    // 16-element forward task, 8 outputs each (split forward phases below)
+    static constexpr bool SPLIT_FWD = THREADS == 512 * CT;
+    static constexpr int FWD_SWEEPS = SPLIT_FWD ? 1 : 256 * CT / THREADS;      // sweeps of the forward phases
     static constexpr int INV_TASKS = 128 * CT;                 // threads with work in the inverse phases
     // Twice as many threads as inverse tasks (the wide shape): every inverse task is shared by two threads of
     // different warps, 8 elements each ("split inverse phases" below) instead of leaving half of the warps idle
     static constexpr bool SPLIT_INV = 2 * INV_TASKS <= THREADS;
     static constexpr int CTAS_PER_SM = CTAS_;                  // default 512 / THREADS: 16 warps per SM at 128 registers
     static constexpr bool TWD_GLOBAL = TWD_GLOBAL_;            // twiddle tables read from global memory / L1, not staged
-    static_assert(FWD_SWEEPS >= 1 && FWD_SWEEPS * THREADS == 256 * CT && INV_TASKS <= THREADS && THREADS % 128 == 0, "shape");
+    static_assert(FWD_SWEEPS >= 1 && (SPLIT_FWD || FWD_SWEEPS * THREADS == 256 * CT) && INV_TASKS <= THREADS && THREADS % 128 == 0, "shape");
 };
 #ifndef NB_BR_THREADS
 #define NB_BR_THREADS (128 * NB_BR_CT)
@@ -140,6 +143,7 @@ constexpr int BR2_CT = NB_BR_CT;                  // ciphertexts per CTA of the 
 constexpr int BR2_THREADS = NB_BR_THREADS;
 using BrDefault = BrCfg<BR2_CT, BR2_THREADS, NB_BR_CTAS, NB_BR_TWD_GLOBAL != 0>;
 using BrWide = BrCfg<1, 256>;
+using BrWide2 = BrCfg<1, 512, 1>;                 // lowest latency: one ciphertext per SM, 16 warps in step
 constexpr int BR2_POLYS = BrDefault::POLYS;
 // Engine bootstrap-key row: 8 planes [(mi*2+j)*2+mo][row*64 + stored column] of plain field values plus
 // 2 correction planes K[mo] = 512 * NTT(1,...,1) * sum_{mi,j} plane, because the forward transforms run
@@ -399,6 +403,104 @@ NB_HD void phase_inv3(int p, int row, int u, u64 *w_all)
     load16_b(v, w, u);
     run_network<NetDit16>(v, [&]() { load16_b(v, w, u); });
     store16_b(v, w, u);
+}
+
+// ---- split forward phases (Cfg::SPLIT_FWD) --------------------------------------------------------------------------
+// The mirror image of the split inverse phases below, without an exchange: a 16-point decimation-in-frequency network
+// is one layer that pairs element k with element 8 + k, followed by two 8-point networks (dif_inlane<3, 24>) on the sums
+// and on the twiddled differences.  Both threads of a task read all 16 inputs; half 0 forms the 8 sums, half 1 the 8
+// differences times 2^(12 k), each runs its 8-point network and stores its 8 outputs.
+template <int H> NB_HD void dif16_half(const u64 *v16, u64 *u8)
+{
+    static_for<0, 8>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        if constexpr (H == 0) u8[k] = ff_add(v16[k], v16[k + 8]);
+        else u8[k] = ff_shl<(12 * k) % 192>(ff_sub(v16[k], v16[k + 8]));
+    });
+    dif_inlane<3, 24, 0>(u8);
+}
+template <bool ROTATE, int H>
+NB_HD void phase_fwd1_split(int task, const i32 *acc_all, u64 *w_all, const u64 *twd, const int *rot_a)
+{
+    const int j2 = task & 63, p = task >> 6;           // p = ct * 4 + mi * 2 + j
+    const int ct = p >> 2, mi = (p >> 1) & 1, j = p & 1;
+    const i32 *acc = acc_all + (ct * 2 + mi) * NTT_N;
+    const int a = ROTATE ? rot_a[ct] : 0;
+    const int ar = a & (NTT_N - 1);
+    const bool flip = (a >> 10) & 1;
+    u64 v[16], u[8];
+    static_for<0, 16>([&](auto J) {
+        constexpr int j1 = decltype(J)::value;
+        const int idx = 64 * j1 + j2;
+        i32 c = ROTATE ? rotate_minus_one(acc, idx, ar, flip) : acc[idx];
+        v[j1] = ff_twist_small<j1>(decomp_udigit(c, j));
+    });
+    dif16_half<H>(v, u);
+    u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15) + 8 * H * ROW_STRIDE;
+    const u64 *tw = twd + 8 * H * 64 + j2;
+    u32 hmax = 0;
+    static_for<0, 8>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+#if NB_LAZY_CANON
+        const u64 x = ff_mul_nc(u[r], tw[r * 64]);
+        hmax = umax32(hmax, hi32(x));
+        w[r * ROW_STRIDE] = x;
+#else
+        w[r * ROW_STRIDE] = ff_mul(u[r], tw[r * 64]);
+#endif
+    });
+#if NB_LAZY_CANON
+    if (canon_needed(hmax)) {
+        static_for<0, 8>([&](auto R) { w[decltype(R)::value * ROW_STRIDE] = ff_canon_almost(w[decltype(R)::value * ROW_STRIDE]); });
+    }
+#endif
+}
+template <int G, int H> NB_HD void fwd2_twiddle_half(u64 *v8)        // v8[a * 2 + e'], e = 2 H + e'
+{
+    static_for<1, 4>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        constexpr int kappa = brev(u, 2);
+        static_for<0, 2>([&](auto E) {
+            constexpr int e = 2 * H + decltype(E)::value;
+            v8[u * 2 + decltype(E)::value] = ff_shl<(3 * kappa * (4 * G + e)) % 192>(v8[u * 2 + decltype(E)::value]);
+        });
+    });
+}
+template <int H> NB_HD void phase_fwd2_split(int p, int row, int g, u64 *w_all)
+{
+    u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[8];
+    static_for<0, 4>([&](auto A) {
+        constexpr int a = decltype(A)::value;
+        ld2(w + 16 * a + 4 * (g ^ a) + 2 * H, v[a * 2], v[a * 2 + 1]);
+    });
+    static_for<0, 2>([&](auto E) { dif_inlane<2, 48, decltype(E)::value, 2>(v); });
+    switch (g) {           // warp-uniform
+    case 0: fwd2_twiddle_half<0, H>(v); break;
+    case 1: fwd2_twiddle_half<1, H>(v); break;
+    case 2: fwd2_twiddle_half<2, H>(v); break;
+    default: fwd2_twiddle_half<3, H>(v); break;
+    }
+    static_for<0, 4>([&](auto A) {
+        constexpr int a = decltype(A)::value;
+        st2(w + 16 * a + 4 * (g ^ a) + 2 * H, v[a * 2], v[a * 2 + 1]);
+    });
+}
+// fwd3 works in place and both halves need all 16 inputs: every thread loads them (phase_fwd3_split_load), the CTA
+// synchronises, and only then each half stores its 8 outputs (phase_fwd3_split_finish)
+NB_HD void phase_fwd3_split_load(int p, int row, int u, const u64 *w_all, u64 *v)
+{
+    load16_b(v, w_all + p * POLY_STRIDE + row * ROW_STRIDE, u);
+}
+template <int H> NB_HD void phase_fwd3_split_finish(int p, int row, int u, u64 *w_all, const u64 *v)
+{
+    u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    u64 o[8];
+    dif16_half<H>(v, o);
+    static_for<0, 4>([&](auto PI) {
+        constexpr int pi = 4 * H + decltype(PI)::value;
+        st2(w + 16 * u + 2 * ((pi ^ (2 * u)) & 7), o[2 * decltype(PI)::value], o[2 * decltype(PI)::value + 1]);
+    });
 }
 
 // ---- split inverse phases (Cfg::SPLIT_INV) --------------------------------------------------------------------------
@@ -729,7 +831,15 @@ template <class Cfg = BrDefault> NB_HD bool map_inv2(int tid, int &p, int &row, 
     return x < 32 * Cfg::CT;
 }
 // split inverse phases: h = thread half (warps 0 .. THREADS/64 - 1: h = 0, the others h = 1), t = task of the unsplit map
-template <class Cfg> NB_HD void map_split(int tid, int &h, int &t) { h = tid >= Cfg::INV_TASKS; t = tid - h * Cfg::INV_TASKS; }
+// (threads beyond twice the task count -- the upper half of the wide2 shape -- have no inverse work: returns false)
+template <class Cfg> NB_HD bool map_split(int tid, int &h, int &t)
+{
+    h = tid >= Cfg::INV_TASKS;
+    t = tid - h * Cfg::INV_TASKS;
+    return tid < 2 * Cfg::INV_TASKS;
+}
+// split forward phases: 256 CT tasks, h = 0 for the lower half of the CTA's threads
+template <class Cfg> NB_HD void map_split_fwd(int tid, int &h, int &t) { h = tid >= 256 * Cfg::CT; t = tid - h * 256 * Cfg::CT; }
 // inv2 tasks of the split phases: t in [0, INV_TASKS), g warp-uniform (32 consecutive tasks per g and polynomial pair)
 template <class Cfg> NB_HD void map_inv2_split(int t, int &p, int &row, int &g)
 {

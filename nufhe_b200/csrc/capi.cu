@@ -17,6 +17,7 @@ struct nb_ctx {
     u64 *d_ones512;                      // 512 * NTT(all-ones), natural order (bk_prepare)
     int sm_count;
     size_t wide_max;                     // largest batch launched in the wide (1 ciphertext / 256 threads) shape
+    size_t wide2_max;                    // largest batch launched in the wide2 (1 ciphertext / 512 threads / SM) shape
     int max_chunks;                      // upper bound on the chunks a chain is cut into (1 = no time slicing)
     unsigned *d_sched;                   // work-queue state of the fused bootstrap (kernels.cuh: BlindRotateArgs)
     size_t sched_words;
@@ -123,6 +124,8 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
                                            (int)br_smem_bytes<BrDefault>()), "cudaFuncSetAttribute(blind_rotate)"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel<BrWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)br_smem_bytes<BrWide>()), "cudaFuncSetAttribute(blind_rotate wide)"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel<BrWide2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)br_smem_bytes<BrWide2>()), "cudaFuncSetAttribute(blind_rotate wide2)"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)KS_SMEM_BYTES), "cudaFuncSetAttribute(keyswitch)"));
     {   // batches that fit one wave of wide CTAs (one ciphertext on 256 threads) take the low-latency shape
@@ -130,6 +133,9 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
         // up to one wave the wide shape has the shortest step; between one and ~1.7 waves it still wins, time-sliced
         // over all SMs, against a throughput-shape launch that leaves half of the SMs with one CTA (r2 sweep)
         ctx->wide_max = e ? (size_t)atoll(e) : (size_t)ctx->sm_count * BrWide::CTAS_PER_SM * 17 / 10;
+        // one ciphertext per SM or fewer: 512 threads per ciphertext, forward phases split as well (lowest latency)
+        e = getenv("NUFHE_B200_WIDE2_MAX");
+        ctx->wide2_max = e ? (size_t)atoll(e) : (size_t)ctx->sm_count;
     }
     NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_I32_BYTES)), "attr"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_U64_BYTES)), "attr"));
@@ -327,6 +333,7 @@ template <class Cfg> static int launch_br_cfg(nb_ctx *ctx, BlindRotateArgs &p)
 // shortest step) while the batch fits one wave of them, else 2 ciphertexts per CTA (highest throughput).
 static int launch_br(nb_ctx *ctx, BlindRotateArgs &p)
 {
+    if (p.batch <= ctx->wide2_max) return launch_br_cfg<BrWide2>(ctx, p);
     if (p.batch <= ctx->wide_max) return launch_br_cfg<BrWide>(ctx, p);
     return launch_br_cfg<BrDefault>(ctx, p);
 }

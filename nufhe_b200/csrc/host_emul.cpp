@@ -106,19 +106,38 @@ template <class Cfg> static void phase_step(i32 *acc_io, const u64 *bk_ref_row, 
         for (int mo = 0; mo < 2; mo++) bk[(8 + mo) * NTT_N + pos] = ff_mul(sum[mo], T.ones512[k]);
     }
     constexpr int TH = Cfg::THREADS;
-    for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
-        for (int tid = 0; tid < TH; tid++) {
-            if (rot) phase_fwd1<true>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
-            else phase_fwd1<false>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
+    if constexpr (Cfg::SPLIT_FWD) {
+        using Tasks = BrCfg<Cfg::CT, 256 * Cfg::CT>;
+        auto each = [&](auto fn) { for (int tid = 0; tid < TH; tid++) { int h, t; map_split_fwd<Cfg>(tid, h, t); fn(h, t); } };
+        each([&](int h, int t) {
+            if (rot) { if (h) phase_fwd1_split<true, 1>(t, acc.data(), w.data(), T.fwd.data(), rots); else phase_fwd1_split<true, 0>(t, acc.data(), w.data(), T.fwd.data(), rots); }
+            else { if (h) phase_fwd1_split<false, 1>(t, acc.data(), w.data(), T.fwd.data(), rots); else phase_fwd1_split<false, 0>(t, acc.data(), w.data(), T.fwd.data(), rots); }
+        });
+        each([&](int h, int t) { int p, r, g; map_fwd2<Tasks>(t, 0, p, r, g); if (h) phase_fwd2_split<1>(p, r, g, w.data()); else phase_fwd2_split<0>(p, r, g, w.data()); });
+        {   // in place: every thread holds its 16 inputs in registers across a barrier
+            std::vector<u64> held((size_t)TH * 16);
+            each([&](int h, int t) { int p, r, u; map_fwd3<Tasks>(t, 0, p, r, u); phase_fwd3_split_load(p, r, u, w.data(), &held[(size_t)(h * 256 * Cfg::CT + t) * 16]); });
+            each([&](int h, int t) {
+                int p, r, u; map_fwd3<Tasks>(t, 0, p, r, u);
+                const u64 *v = &held[(size_t)(h * 256 * Cfg::CT + t) * 16];
+                if (h) phase_fwd3_split_finish<1>(p, r, u, w.data(), v); else phase_fwd3_split_finish<0>(p, r, u, w.data(), v);
+            });
         }
-    for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
-        for (int tid = 0; tid < TH; tid++) { int p, r, g; map_fwd2<Cfg>(tid, it, p, r, g); phase_fwd2(p, r, g, w.data()); }
-    for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
-        for (int tid = 0; tid < TH; tid++) { int p, r, u; map_fwd3<Cfg>(tid, it, p, r, u); phase_fwd3(p, r, u, w.data()); }
+    } else {
+        for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
+            for (int tid = 0; tid < TH; tid++) {
+                if (rot) phase_fwd1<true>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
+                else phase_fwd1<false>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
+            }
+        for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
+            for (int tid = 0; tid < TH; tid++) { int p, r, g; map_fwd2<Cfg>(tid, it, p, r, g); phase_fwd2(p, r, g, w.data()); }
+        for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
+            for (int tid = 0; tid < TH; tid++) { int p, r, u; map_fwd3<Cfg>(tid, it, p, r, u); phase_fwd3(p, r, u, w.data()); }
+    }
     for (int tid = 0; tid < TH; tid++) phase_mac<Cfg>(tid, w.data(), bk.data());
     if constexpr (Cfg::SPLIT_INV) {
         // the split inverse phases of the wide shape, one loop per barrier-separated sub-pass (kernels.cuh: br2_step)
-        auto each = [&](auto fn) { for (int tid = 0; tid < TH; tid++) { int h, t; map_split<Cfg>(tid, h, t); fn(h, t); } };
+        auto each = [&](auto fn) { for (int tid = 0; tid < TH; tid++) { int h, t; if (map_split<Cfg>(tid, h, t)) fn(h, t); } };
         each([&](int h, int t) { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_a<1>(p, r, u, w.data()); else phase_inv3_split_a<0>(p, r, u, w.data()); });
         each([&](int h, int t) { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_b<1>(p, r, u, w.data()); else phase_inv3_split_b<0>(p, r, u, w.data()); });
         each([&](int h, int t) { int p, r, g; map_inv2_split<Cfg>(t, p, r, g); if (h) phase_inv2_split<1>(p, r, g, w.data()); else phase_inv2_split<0>(p, r, g, w.data()); });
@@ -148,6 +167,11 @@ void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct
 void emul_phase_step_wide(i32 *acc_io, const u64 *bk_ref_row, const int *rot)
 {
     phase_step<BrWide>(acc_io, bk_ref_row, rot, 1);
+}
+// the wide2 shape (one ciphertext on 512 threads: split forward and inverse phases)
+void emul_phase_step_wide2(i32 *acc_io, const u64 *bk_ref_row, const int *rot)
+{
+    phase_step<BrWide2>(acc_io, bk_ref_row, rot, 1);
 }
 
 void emul_ff_shl_var(const u64 *in, const int *s, u64 *out, size_t n)

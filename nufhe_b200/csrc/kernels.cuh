@@ -340,15 +340,35 @@ template <bool ROTATE, class Cfg>
 NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *rot, int tid)
 {
     // forward transforms of the digit polynomials (CT ciphertexts x 2 polynomials x 2 digits)
+    if constexpr (Cfg::SPLIT_FWD) {
+        // two threads (of different warps) per task, 8 outputs each; tasks mapped as in the 256-thread shape
+        using Tasks = BrCfg<Cfg::CT, 256 * Cfg::CT>;
+        int h, t;
+        map_split_fwd<Cfg>(tid, h, t);
+        if (h) phase_fwd1_split<ROTATE, 1>(t, s.acc, s.w, s.twd_fwd, rot); else phase_fwd1_split<ROTATE, 0>(t, s.acc, s.w, s.twd_fwd, rot);
+        __syncthreads();
+        { int p, r, g; map_fwd2<Tasks>(t, 0, p, r, g); if (h) phase_fwd2_split<1>(p, r, g, s.w); else phase_fwd2_split<0>(p, r, g, s.w); }
+        __syncthreads();
+        {
+            int p, r, u;
+            u64 v[16];
+            map_fwd3<Tasks>(t, 0, p, r, u);
+            phase_fwd3_split_load(p, r, u, s.w, v);
+            __syncthreads();                               // in place: all loads before any store
+            if (h) phase_fwd3_split_finish<1>(p, r, u, s.w, v); else phase_fwd3_split_finish<0>(p, r, u, s.w, v);
+        }
+        __syncthreads();
+    } else {
 #pragma unroll 1
-    for (int it = 0; it < Cfg::FWD_SWEEPS; it++) phase_fwd1<ROTATE>(it * Cfg::THREADS + tid, s.acc, s.w, s.twd_fwd, rot);
-    __syncthreads();
+        for (int it = 0; it < Cfg::FWD_SWEEPS; it++) phase_fwd1<ROTATE>(it * Cfg::THREADS + tid, s.acc, s.w, s.twd_fwd, rot);
+        __syncthreads();
 #pragma unroll 1
-    for (int it = 0; it < Cfg::FWD_SWEEPS; it++) { int p, r, g; map_fwd2<Cfg>(tid, it, p, r, g); phase_fwd2(p, r, g, s.w); }
-    __syncthreads();
+        for (int it = 0; it < Cfg::FWD_SWEEPS; it++) { int p, r, g; map_fwd2<Cfg>(tid, it, p, r, g); phase_fwd2(p, r, g, s.w); }
+        __syncthreads();
 #pragma unroll 1
-    for (int it = 0; it < Cfg::FWD_SWEEPS; it++) { int p, r, u; map_fwd3<Cfg>(tid, it, p, r, u); phase_fwd3(p, r, u, s.w); }
-    __syncthreads();
+        for (int it = 0; it < Cfg::FWD_SWEEPS; it++) { int p, r, u; map_fwd3<Cfg>(tid, it, p, r, u); phase_fwd3(p, r, u, s.w); }
+        __syncthreads();
+    }
     // multiply-accumulate with the key row (tgsw_gpu.py:58-107); each key element is fetched once per CTA
     phase_mac<Cfg>(tid, s.w, bk_row);
     __syncthreads();
@@ -357,16 +377,16 @@ NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *
         // twice as many threads as tasks: two threads (of different warps) per task, 8 elements each, parked values
         // exchanged through the dead work polynomials (br_phases.cuh: split inverse phases); two more barriers
         int h, t;
-        map_split<Cfg>(tid, h, t);
-        { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_a<1>(p, r, u, s.w); else phase_inv3_split_a<0>(p, r, u, s.w); }
+        const bool act = map_split<Cfg>(tid, h, t);      // whole warps either way
+        if (act) { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_a<1>(p, r, u, s.w); else phase_inv3_split_a<0>(p, r, u, s.w); }
         __syncthreads();
-        { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_b<1>(p, r, u, s.w); else phase_inv3_split_b<0>(p, r, u, s.w); }
+        if (act) { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_b<1>(p, r, u, s.w); else phase_inv3_split_b<0>(p, r, u, s.w); }
         __syncthreads();
-        { int p, r, g; map_inv2_split<Cfg>(t, p, r, g); if (h) phase_inv2_split<1>(p, r, g, s.w); else phase_inv2_split<0>(p, r, g, s.w); }
+        if (act) { int p, r, g; map_inv2_split<Cfg>(t, p, r, g); if (h) phase_inv2_split<1>(p, r, g, s.w); else phase_inv2_split<0>(p, r, g, s.w); }
         __syncthreads();
-        if (h) phase_inv1_split_a<1>(t, s.w, s.twd_inv); else phase_inv1_split_a<0>(t, s.w, s.twd_inv);
+        if (act) { if (h) phase_inv1_split_a<1>(t, s.w, s.twd_inv); else phase_inv1_split_a<0>(t, s.w, s.twd_inv); }
         __syncthreads();
-        if (h) phase_inv1_split_b<ROTATE, 1>(t, s.acc, s.w); else phase_inv1_split_b<ROTATE, 0>(t, s.acc, s.w);
+        if (act) { if (h) phase_inv1_split_b<ROTATE, 1>(t, s.acc, s.w); else phase_inv1_split_b<ROTATE, 0>(t, s.acc, s.w); }
     } else {
         // (threads beyond Cfg::INV_TASKS idle: whole warps)
         { int p, r, u; if (map_inv3<Cfg>(tid, p, r, u)) phase_inv3(p, r, u, s.w); }

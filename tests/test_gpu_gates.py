@@ -117,29 +117,33 @@ def test_full_size_batches_decrypt_to_truth_table(eng, keys, dev_keys, batch):
     assert (keys.decrypt((eng.to_host(ma), eng.to_host(mb))) == numpy.where(bits[0], bits[1], bits[2])).all()
 
 
-def test_both_cta_shapes_give_the_same_bits(keys, monkeypatch):
-    """The fused kernel has two CTA shapes (2 ciphertexts per 256 threads; 1 ciphertext per 256 threads for batches
-    that fit one wave).  Force each shape for the same inputs, including a ragged batch and one larger than a wave
-    of wide CTAs; both must equal the oracle."""
+def test_all_cta_shapes_give_the_same_bits(keys, monkeypatch):
+    """The fused kernel has three CTA shapes: 2 ciphertexts per 256 threads (throughput), 1 ciphertext per 256 threads
+    (inverse phases split over thread pairs) and 1 ciphertext per 512 threads (forward phases split as well; batches
+    up to one ciphertext per SM).  Force each shape for the same inputs, including a ragged batch and one larger than
+    a wave of the wide CTAs (time-sliced); all must equal the oracle and each other."""
     from nufhe_b200.engine import Engine
     rng = G.rs(480)
-    outs = {}
+    shapes = {'default': ('0', '0'), 'wide': ('1000000', '0'), 'wide2': ('1000000', '1000000')}
     for B in (1, 5, 301):
         bits_a, bits_b = rng.randint(0, 2, B).astype(bool), rng.randint(0, 2, B).astype(bool)
         a, b = keys.encrypt(bits_a), keys.encrypt(bits_b)
         want = O.gate_binary('nand', a, b, keys.bk, keys.ks) if B <= 5 else None
-        for wide_max in ('0', '1000000'):
+        outs = {}
+        for name, (wide_max, wide2_max) in shapes.items():
             monkeypatch.setenv('NUFHE_B200_WIDE_MAX', wide_max)
+            monkeypatch.setenv('NUFHE_B200_WIDE2_MAX', wide2_max)
             eng = Engine()
             dk = (eng.bk_prepare(eng.to_device(keys.bk)),
                   (eng.to_device(keys.ks_a), eng.to_device(keys.ks_b), eng.to_device(keys.ks_cv)))
             ext, out = gpu_gate(eng, dk, 'nand', a, b)
-            outs[(B, wide_max)] = (ext, out)
+            outs[name] = (ext, out)
             if want is not None:
-                assert (out[0] == want[0]).all() and (out[1] == want[1]).all(), (B, wide_max)
+                assert (out[0] == want[0]).all() and (out[1] == want[1]).all(), (B, name)
             assert (keys.decrypt(out) == ~(bits_a & bits_b)).all()
-        for x, y in zip(outs[(B, '0')], outs[(B, '1000000')]):
-            assert (x[0] == y[0]).all() and (x[1] == y[1]).all(), B
+        for name in ('wide', 'wide2'):
+            for x, y in zip(outs['default'], outs[name]):
+                assert (x[0] == y[0]).all() and (x[1] == y[1]).all(), (B, name)
 
 
 # ---- BASELINE.md section 4 parity set --------------------------------------------------------------------------
@@ -268,7 +272,7 @@ print('rare path ok')
 '''
 
 
-@pytest.mark.parametrize('wide_max', ['0', '1000000'])
+@pytest.mark.parametrize('wide_max', ['0', '1000000', 'wide2'])
 def test_canonicalisation_rare_path_forced(wide_max):
     """NUFHE_B200_FORCE_RARE_PATH=1 lowers the trigger of the deferred canonicalisation so that EVERY task of fwd1,
     inv1 and the MAC runs its fix-up code (normally 2^-32 per element); results must not change.  Runs in a fresh
@@ -277,7 +281,9 @@ def test_canonicalisation_rare_path_forced(wide_max):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, NUFHE_B200_FORCE_RARE_PATH='1', NUFHE_B200_WIDE_MAX=wide_max)
+    env = dict(os.environ, NUFHE_B200_FORCE_RARE_PATH='1')
+    env.update({'NUFHE_B200_WIDE_MAX': '1000000', 'NUFHE_B200_WIDE2_MAX': '1000000'} if wide_max == 'wide2' else
+               {'NUFHE_B200_WIDE_MAX': wide_max, 'NUFHE_B200_WIDE2_MAX': '0'})
     r = subprocess.run([sys.executable, '-c', _RARE_PATH_SCRIPT % {'root': root}], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and 'rare path ok' in r.stdout, r.stdout + r.stderr

@@ -248,16 +248,18 @@ def test_phase_structured_step_matches_oracle(emul):
         a = acc.copy()
         emul.emul_phase_step(_p(a), _p(bk[0]), _p(rot), ctypes.c_int(nct))
         assert (a == O.blind_rotate(acc, bk[0:1], rot.reshape(nct, 1))).all()
-    # the wide CTA shape (one ciphertext on 256 threads, used for small batches): same phases, other task maps
-    for r in (0, 5, 1024, 2047):
-        acc = G.torus32(rng, (1, 2, 1024))
-        a = acc.copy()
-        emul.emul_phase_step_wide(_p(a), _p(bk[1]), None)
-        assert (a == O.tgsw_external_mul(acc, bk, 1)).all()
-        rot = numpy.array([r], numpy.int32)
-        a = acc.copy()
-        emul.emul_phase_step_wide(_p(a), _p(bk[0]), _p(rot))
-        assert (a == O.blind_rotate(acc, bk[0:1], rot.reshape(1, 1))).all()
+    # the wide CTA shapes (one ciphertext on 256 / 512 threads, used for small batches): the inverse phases -- and in
+    # the 512-thread shape also the forward phases -- run split, two threads per 16-element task, 8 elements each
+    for step in (emul.emul_phase_step_wide, emul.emul_phase_step_wide2):
+        for r in (0, 5, 1024, 2047):
+            acc = G.torus32(rng, (1, 2, 1024))
+            a = acc.copy()
+            step(_p(a), _p(bk[1]), None)
+            assert (a == O.tgsw_external_mul(acc, bk, 1)).all()
+            rot = numpy.array([r], numpy.int32)
+            a = acc.copy()
+            step(_p(a), _p(bk[0]), _p(rot))
+            assert (a == O.blind_rotate(acc, bk[0:1], rot.reshape(1, 1))).all()
 
 
 def test_uint_bit_helpers_roundtrip():
