@@ -133,9 +133,10 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
         // up to one wave the wide shape has the shortest step; between one and ~1.7 waves it still wins, time-sliced
         // over all SMs, against a throughput-shape launch that leaves half of the SMs with one CTA (r2 sweep)
         ctx->wide_max = e ? (size_t)atoll(e) : (size_t)ctx->sm_count * BrWide::CTAS_PER_SM * 17 / 10;
-        // one ciphertext per SM or fewer: 512 threads per ciphertext, forward phases split as well (lowest latency)
+        // up to 1.5 ciphertexts per SM: 512 threads per ciphertext, forward phases split as well (lowest latency;
+        // measured crossover against the 256-thread shape between 200 and 296 ciphertexts, profiles/r2_variants.md)
         e = getenv("NUFHE_B200_WIDE2_MAX");
-        ctx->wide2_max = e ? (size_t)atoll(e) : (size_t)ctx->sm_count;
+        ctx->wide2_max = e ? (size_t)atoll(e) : (size_t)ctx->sm_count * 3 / 2;
     }
     NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_I32_BYTES)), "attr"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_U64_BYTES)), "attr"));
