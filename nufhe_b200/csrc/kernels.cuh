@@ -377,16 +377,25 @@ NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *
         // twice as many threads as tasks: two threads (of different warps) per task, 8 elements each, parked values
         // exchanged through the dead work polynomials (br_phases.cuh: split inverse phases); two more barriers
         int h, t;
-        const bool act = map_split<Cfg>(tid, h, t);      // whole warps either way
-        if (act) { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_a<1>(p, r, u, s.w); else phase_inv3_split_a<0>(p, r, u, s.w); }
-        __syncthreads();
-        if (act) { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_b<1>(p, r, u, s.w); else phase_inv3_split_b<0>(p, r, u, s.w); }
-        __syncthreads();
-        if (act) { int p, r, g; map_inv2_split<Cfg>(t, p, r, g); if (h) phase_inv2_split<1>(p, r, g, s.w); else phase_inv2_split<0>(p, r, g, s.w); }
-        __syncthreads();
-        if (act) { if (h) phase_inv1_split_a<1>(t, s.w, s.twd_inv); else phase_inv1_split_a<0>(t, s.w, s.twd_inv); }
-        __syncthreads();
-        if (act) { if (h) phase_inv1_split_b<ROTATE, 1>(t, s.acc, s.w); else phase_inv1_split_b<ROTATE, 0>(t, s.acc, s.w); }
+        // threads beyond twice the task count (the upper half of the wide2 CTA, whole warps) have no inverse work: they
+        // go straight to the barrier that ends the step, and the working warps synchronise among themselves on a
+        // named barrier
+        if (map_split<Cfg>(tid, h, t)) {
+            constexpr int WORKERS = 2 * Cfg::INV_TASKS;
+            auto sync_workers = [] {
+                if constexpr (WORKERS == Cfg::THREADS) __syncthreads();
+                else asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
+            };
+            { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_a<1>(p, r, u, s.w); else phase_inv3_split_a<0>(p, r, u, s.w); }
+            sync_workers();
+            { int p, r, u; map_inv3<Cfg>(t, p, r, u); if (h) phase_inv3_split_b<1>(p, r, u, s.w); else phase_inv3_split_b<0>(p, r, u, s.w); }
+            sync_workers();
+            { int p, r, g; map_inv2_split<Cfg>(t, p, r, g); if (h) phase_inv2_split<1>(p, r, g, s.w); else phase_inv2_split<0>(p, r, g, s.w); }
+            sync_workers();
+            if (h) phase_inv1_split_a<1>(t, s.w, s.twd_inv); else phase_inv1_split_a<0>(t, s.w, s.twd_inv);
+            sync_workers();
+            if (h) phase_inv1_split_b<ROTATE, 1>(t, s.acc, s.w); else phase_inv1_split_b<ROTATE, 0>(t, s.acc, s.w);
+        }
     } else {
         // (threads beyond Cfg::INV_TASKS idle: whole warps)
         { int p, r, u; if (map_inv3<Cfg>(tid, p, r, u)) phase_inv3(p, r, u, s.w); }

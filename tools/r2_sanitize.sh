@@ -8,5 +8,4 @@ for tool in memcheck synccheck; do
 done
 SANITIZE_BATCH=620 timeout 1500 compute-sanitizer --tool racecheck --racecheck-report analysis --print-limit 2000 python tools/sanitize_target.py > $O/racecheck_all.txt 2>&1
 tail -3 $O/racecheck_all.txt
-grep -o "in kernel [A-Za-z_0-9:<>, ]*\|at .* in [a-z_0-9]*kernel[^(]*" $O/racecheck_all.txt | sort | uniq -c | sort -rn | head -20
-grep -c "hazard" $O/racecheck_all.txt
+grep -o "in [a-z_0-9:]*kernel[^ (]*\|at nb::[a-z_0-9]*" $O/racecheck_all.txt | sort | uniq -c | sort -rn | head -10
