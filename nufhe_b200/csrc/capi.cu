@@ -355,6 +355,7 @@ int nb_ctx_reserve(nb_ctx *ctx, size_t batch)
 
 int nb_external_product(nb_ctx *ctx, int32_t *accum, const uint64_t *bk_int, size_t bk_row, size_t batch)
 {
+    if (ctx && batch == 0) return NB_OK;     // nothing to do: empty arrays have no storage to check
     if (!ctx || !accum || !bk_int) return fail(ctx, NB_EINVAL, "nb_external_product: null argument");
     if (batch == 0) return NB_OK;
     NB_ON_DEVICE(ctx);
@@ -379,6 +380,7 @@ static int launch_blind_rotate(nb_ctx *ctx, BlindRotateArgs &p)
 int nb_blind_rotate(nb_ctx *ctx, const int32_t *accum, const int32_t *bara, const uint64_t *bk_int, size_t n,
                     int32_t *out_a, int32_t *out_b, int32_t *accum_out, size_t batch)
 {
+    if (ctx && batch == 0) return NB_OK;     // nothing to do: empty arrays have no storage to check
     if (!ctx || !accum || !bara || !bk_int) return fail(ctx, NB_EINVAL, "nb_blind_rotate: null argument");
     if ((out_a == nullptr) != (out_b == nullptr)) return fail(ctx, NB_EINVAL, "nb_blind_rotate: out_a/out_b must come together");
     BlindRotateArgs p{};
@@ -391,6 +393,7 @@ int nb_bootstrap_extract(nb_ctx *ctx, const int32_t *in1_a, const int32_t *in1_b
                          const int32_t *in2_b, int32_t c, int32_t s1, int32_t s2, int32_t mu,
                          const uint64_t *bk_int, size_t n, int32_t *out_a, int32_t *out_b, size_t batch)
 {
+    if (ctx && batch == 0) return NB_OK;     // nothing to do: empty arrays have no storage to check
     if (!ctx || !in1_a || !in1_b || !bk_int || !out_a || !out_b)
         return fail(ctx, NB_EINVAL, "nb_bootstrap_extract: null argument");
     if ((in2_a == nullptr) != (in2_b == nullptr)) return fail(ctx, NB_EINVAL, "nb_bootstrap_extract: in2_a/in2_b must come together");
@@ -407,6 +410,7 @@ int nb_bootstrap_extract2(nb_ctx *ctx, const int32_t *a1_a, const int32_t *a1_b,
                           int32_t b_s2, int32_t mu, const uint64_t *bk_int, size_t n, int32_t *out_a, int32_t *out_b,
                           size_t batch)
 {
+    if (ctx && batch == 0) return NB_OK;     // nothing to do: empty arrays have no storage to check
     if (!ctx || !a1_a || !a1_b || !b1_a || !b1_b || !bk_int || !out_a || !out_b)
         return fail(ctx, NB_EINVAL, "nb_bootstrap_extract2: null argument");
     if ((a2_a == nullptr) != (a2_b == nullptr) || (b2_a == nullptr) != (b2_b == nullptr))
@@ -424,6 +428,7 @@ int nb_keyswitch(nb_ctx *ctx, const int32_t *src1_a, const int32_t *src1_b, cons
                  size_t in_size, size_t n, int t, int log2_base, int32_t *res_a, int32_t *res_b, float *res_cv,
                  size_t batch)
 {
+    if (ctx && batch == 0) return NB_OK;     // nothing to do: empty arrays have no storage to check
     if (!ctx || !src1_a || !src1_b || !ks_a || !ks_b || !ks_cv || !res_a || !res_b)
         return fail(ctx, NB_EINVAL, "nb_keyswitch: null argument");
     if ((src2_a == nullptr) != (src2_b == nullptr)) return fail(ctx, NB_EINVAL, "nb_keyswitch: src2_a/src2_b must come together");
@@ -569,6 +574,7 @@ int nb_lwe_affine(nb_ctx *ctx, int32_t *res_a, int32_t *res_b, const int32_t *x1
                   const int32_t *x2_a, const int32_t *x2_b, int32_t c, int32_t s1, int32_t s2, size_t batch,
                   size_t n)
 {
+    if (ctx && batch == 0) return NB_OK;     // nothing to do: empty arrays have no storage to check
     if (!ctx || !res_a || !res_b) return fail(ctx, NB_EINVAL, "nb_lwe_affine: null argument");
     if ((x1_a == nullptr) != (x1_b == nullptr) || (x2_a == nullptr) != (x2_b == nullptr))
         return fail(ctx, NB_EINVAL, "nb_lwe_affine: a/b parts must come together");
@@ -584,6 +590,7 @@ int nb_lwe_dot(nb_ctx *ctx, int32_t *out, const int32_t *a, const int32_t *key, 
                const int32_t *add2, int32_t sign, size_t batch, size_t n)
 {
     if (!ctx) return NB_EINVAL;
+    if (batch == 0) return NB_OK;
     if (!out || !a || !key) return fail(ctx, NB_EINVAL, "nb_lwe_dot: null argument");
     if (n == 0 || n > (1u << 30)) return fail(ctx, NB_EINVAL, "nb_lwe_dot: bad LWE dimension");
     if (batch == 0) return NB_OK;

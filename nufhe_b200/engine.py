@@ -141,7 +141,7 @@ class Engine:
         accum = self._dense(accum, torch.int32)
         bara = self._dense(bara, torch.int32)
         B = accum.numel() // (2 * N)
-        n = bara.numel() // B
+        n = bara.shape[-1]                    # (an empty batch is a no-op in the library)
         out_a = self.empty((B, N), torch.int32) if extract else None
         out_b = self.empty((B,), torch.int32) if extract else None
         acc_out = torch.empty_like(accum) if return_accum else None
@@ -159,7 +159,7 @@ class Engine:
             a2 = self._dense(x2[0], torch.int32)
             b2 = self._dense(x2[1], torch.int32)
         B = b1.numel()
-        n = a1.numel() // B
+        n = a1.shape[-1]
         out_a, out_b = out if out is not None else (self.empty((B, N), torch.int32), self.empty((B,), torch.int32))
         self._call('nb_bootstrap_extract', _ptr(a1), _ptr(b1), _ptr(a2), _ptr(b2), int(c), int(s1), int(s2),
                    int(mu), _ptr(bk_int), n, _ptr(out_a), _ptr(out_b), B)
@@ -177,7 +177,7 @@ class Engine:
             return a1, b1, a2, b2, int(c), int(s1), int(s2)
         pa, pb = parts(job_a), parts(job_b)
         B = pa[1].numel()
-        n = pa[0].numel() // B
+        n = pa[0].shape[-1]
         out_a, out_b = self.empty((2 * B, N), torch.int32), self.empty((2 * B,), torch.int32)
         self._call('nb_bootstrap_extract2', _ptr(pa[0]), _ptr(pa[1]), _ptr(pa[2]), _ptr(pa[3]), pa[4], pa[5], pa[6],
                    _ptr(pb[0]), _ptr(pb[1]), _ptr(pb[2]), _ptr(pb[3]), pb[4], pb[5], pb[6], int(mu), _ptr(bk_int), n,
@@ -296,7 +296,7 @@ class Engine:
     def lwe_affine(self, res, x1, x2, c, s1, s2):
         res_a, res_b = res
         B = res_b.numel()
-        n = res_a.numel() // B
+        n = res_a.shape[-1]
         a1 = b1 = a2 = b2 = None
         if x1 is not None:
             a1, b1 = self._dense(x1[0], torch.int32), self._dense(x1[1], torch.int32)

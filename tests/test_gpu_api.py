@@ -201,6 +201,18 @@ def test_uint_min_circuit(ctx, key_pair):
     assert (got == numpy.minimum(xs, ys)).all()
 
 
+def test_empty_batch_is_a_no_op(ctx, key_pair, nufhe):
+    """Zero ciphertexts: every gate returns an empty ciphertext without launching anything."""
+    sk, ck = key_pair
+    vm = ctx.make_virtual_machine(ck)
+    a = ctx.encrypt(sk, numpy.zeros((0,), bool))
+    b = ctx.encrypt(sk, numpy.zeros((0,), bool))
+    assert vm.gate_nand(a, b).shape == (0,)
+    assert vm.gate_mux(a, b, a).shape == (0,)
+    assert vm.gate_not(a).shape == (0,)
+    assert ctx.decrypt(sk, vm.gate_xor(a, b)).shape == (0,)
+
+
 def test_uint_min_as_one_cuda_graph(ctx, key_pair):
     """The same circuit (8 x (XNOR + MUX) + MUX = 17 gates, ~60 launches / copies / fills) recorded once with
     VirtualMachine.capture and replayed as ONE graph launch: bit-identical to the eager run, and again after the
