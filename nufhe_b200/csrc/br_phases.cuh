@@ -31,6 +31,9 @@ namespace nb {
 #ifndef NB_BR_CT
 #define NB_BR_CT 2
 #endif
+#ifndef NB_BR_STAGE_KEY
+#define NB_BR_STAGE_KEY 0
+#endif
 // Deferred canonicalisation: the general multiplications of fwd1 / inv1 and the MAC leave their result as "some
 // 64-bit value of the right residue" (ff_mul_nc, ff_dot4_sub_nc) instead of paying 6 ALU instructions per element
 // for the conditional subtraction of p.  Such a value is above p with probability 2^-32 (a few elements per
@@ -128,6 +131,12 @@ template <int CT_, int THREADS_, int CTAS_ = 512 / THREADS_, bool TWD_GLOBAL_ = 
     static constexpr bool SPLIT_INV = 2 * INV_TASKS <= THREADS;
     static constexpr int CTAS_PER_SM = CTAS_;                  // default 512 / THREADS: 16 warps per SM at 128 registers
     static constexpr bool TWD_GLOBAL = TWD_GLOBAL_;            // twiddle tables read from global memory / L1, not staged
+    // EXPERIMENT, off by default (NB_BR_STAGE_KEY, profiles/r2_variants.md section 7): warps without inverse work (the
+    // upper half of the 512-thread shape) stage the key row of the NEXT step in shared memory while the others run the
+    // inverse phases, and the MAC reads shared memory instead of the L2.  What makes the pair shape fast does nothing
+    // here: 16 warps per SM already hide the L2 latency of the MAC (batch 1 / 148 / 222: 3.99 / 4.64 / 6.92 ms with
+    // it, 4.09 / 4.53 / 6.77 without).
+    static constexpr bool STAGE_KEY = NB_BR_STAGE_KEY && SPLIT_INV && THREADS > 2 * INV_TASKS;
     static_assert(FWD_SWEEPS >= 1 && (SPLIT_FWD || FWD_SWEEPS * THREADS == 256 * CT) && INV_TASKS <= THREADS && THREADS % 128 == 0, "shape");
 };
 #ifndef NB_BR_THREADS
@@ -531,14 +540,23 @@ template <int H> NB_HD void dit16_half_b(const u64 *a, const u64 *t, u64 *o)
 }
 
 // inv3, first half: task (p, row, u), elements 8 H .. 8 H + 7 of block u (logical pairs 4 H .. 4 H + 3)
-template <int H> NB_HD void phase_inv3_split_a(int p, int row, int u, u64 *w_all)
+// ADD_PARKED (pair shape): the polynomial to transform is the sum of W[p] and what the peer CTA left in W[p + 2]; the
+// parked values then overwrite the peer's contribution at the very positions this thread has just read
+template <int H, bool ADD_PARKED = false> NB_HD void phase_inv3_split_a(int p, int row, int u, u64 *w_all)
 {
     const u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
     u64 *x = w_all + (p + 2) * POLY_STRIDE + row * ROW_STRIDE;
     u64 v[8];
     static_for<0, 4>([&](auto PI) {
         constexpr int pi = 4 * H + decltype(PI)::value;
-        ld2(w + 16 * u + 2 * ((pi ^ (2 * u)) & 7), v[2 * decltype(PI)::value], v[2 * decltype(PI)::value + 1]);
+        constexpr int k = 2 * decltype(PI)::value;
+        ld2(w + 16 * u + 2 * ((pi ^ (2 * u)) & 7), v[k], v[k + 1]);
+        if constexpr (ADD_PARKED) {
+            u64 r0, r1;
+            ld2(x + 16 * u + 2 * ((pi ^ (2 * u)) & 7), r0, r1);
+            v[k] = ff_add(v[k], r0);
+            v[k + 1] = ff_add(v[k + 1], r1);
+        }
     });
     dit16_half_a<H>(v);
     static_for<0, 4>([&](auto PI) {
@@ -620,7 +638,8 @@ template <int H> NB_HD void phase_inv1_split_a(int task, u64 *w_all, const u64 *
     dit16_half_a<H>(v);
     static_for<0, 8>([&](auto R) { x[decltype(R)::value * ROW_STRIDE] = v[decltype(R)::value]; });
 }
-template <bool ACCUMULATE, int H> NB_HD void phase_inv1_split_b(int task, i32 *acc_all, const u64 *w_all)
+// acc_poly >= 0 (pair shape): the accumulator polynomial to update, instead of polynomial pp of acc_all
+template <bool ACCUMULATE, int H> NB_HD void phase_inv1_split_b(int task, i32 *acc_all, const u64 *w_all, int acc_poly = -1)
 {
     const int j2 = task & 63, pp = task >> 6;
     const int ct = pp >> 1, mo = pp & 1;
@@ -632,7 +651,7 @@ template <bool ACCUMULATE, int H> NB_HD void phase_inv1_split_b(int task, i32 *a
         t[k] = x[(8 + k) * ROW_STRIDE];
     });
     dit16_half_b<H>(a, t, o);
-    i32 *acc = acc_all + (ct * 2 + mo) * NTT_N;
+    i32 *acc = acc_all + (acc_poly >= 0 ? acc_poly : ct * 2 + mo) * NTT_N;
     static_for<0, 8>([&](auto K) {
         constexpr int j1 = 8 * H + decltype(K)::value;
         const int idx = 64 * j1 + j2;
@@ -649,7 +668,7 @@ template <bool ACCUMULATE, int H> NB_HD void phase_inv1_split_b(int task, i32 *a
 // ---- MAC: thread = (row, pair q): stored columns 2q, 2q+1 of every work polynomial -----------------
 // bk_row: internal layout [mi][j][mo][row * 64 + stored column], plain (non-Montgomery) values.
 // out polynomial mo of ciphertext ct overwrites work polynomial ct*4 + mo.
-template <int CT> NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64 *bk_row)
+template <int CT, bool KEY_SHARED = false> NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64 *bk_row)
 {
     const int pos = row * 64 + 2 * q;
 #ifdef NB_BK_L1_BOUND
@@ -662,7 +681,8 @@ template <int CT> NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64
     u64 bk[BK_PLANES][2];
     static_for<0, BK_PLANES>([&](auto M) {
         constexpr int m = decltype(M)::value;            // m = (mi * 2 + j) * 2 + mo; 8 + mo = correction
-        ld2_global(bk_row + m * NTT_N + kpos, bk[m][0], bk[m][1]);
+        if constexpr (KEY_SHARED) ld2(bk_row + m * NTT_N + kpos, bk[m][0], bk[m][1]);
+        else ld2_global(bk_row + m * NTT_N + kpos, bk[m][0], bk[m][1]);
     });
     for (int ct = 0; ct < CT; ct++) {
         u64 *w = w_all + ct * 4 * POLY_STRIDE + row * ROW_STRIDE + 2 * q;
@@ -709,9 +729,130 @@ template <int CT> NB_HD void phase_mac_row(int row, int q, u64 *w_all, const u64
 }
 
 // all 16 rows x 32 pairs, Cfg::THREADS threads
-template <class Cfg = BrDefault> NB_HD void phase_mac(int tid, u64 *w_all, const u64 *bk_row)
+template <class Cfg = BrDefault, bool KEY_SHARED = false> NB_HD void phase_mac(int tid, u64 *w_all, const u64 *bk_row)
 {
-    for (int row = tid >> 5; row < 16; row += Cfg::THREADS / 32) phase_mac_row<Cfg::CT>(row, tid & 31, w_all, bk_row);
+    for (int row = tid >> 5; row < 16; row += Cfg::THREADS / 32) phase_mac_row<Cfg::CT, KEY_SHARED>(row, tid & 31, w_all, bk_row);
+}
+
+// ---- pair shape: one ciphertext on a cluster of two CTAs (two SMs), 256 threads each ---------------------------------
+// CTA `rank` (= mi) owns accumulator polynomial mi: it decomposes it into its two digit polynomials (W[0], W[1]),
+// transforms them (split forward phases, 128 tasks x 2 halves), and multiplies them with the four key planes
+// (mi, j, mo): two partial sums per point, one for each output polynomial.  The partial sum for its OWN output
+// polynomial (mo = rank) stays in W[par]; the other one goes into the peer's W[par + 2] through distributed shared
+// memory, par = step parity.  After one cluster barrier each CTA adds what it received to what it kept (fused into the
+// first inverse pass), runs the inverse transform of its output polynomial (split inverse phases on 128 of the 256
+// threads, W[par + 2] doubling as the exchange area like in the single-CTA shapes) and updates its accumulator polynomial:
+// everything but the exchange of 8 KB per step and direction is local to a CTA.  Alternating par is what makes the
+// exchange safe without a second synchronisation per step: the peer's next remote stores (into W[(par ^ 1) + 2]) can
+// start while this CTA is still in the inverse phases of the current step (W[par], W[par + 2]); the stores after those
+// need this CTA's next partial sums first, which it sends after finishing the current step.
+// The correction plane of the unsigned digits (BK planes 8, 9) is subtracted by rank 0 alone.
+// The per-thread instruction stream is that of the 512-thread shape, but each SM carries 8 warps instead of 16.
+constexpr int PAIR_THREADS = 256;
+constexpr int PAIR_POLYS = 4;
+constexpr int PAIR_INV_WORKERS = 128;                 // threads with work in the inverse phases (64 tasks x 2 halves)
+
+NB_HD void pair_fwd1(int tid, const i32 *acc, u64 *w, const u64 *twd, const int *rot)
+{
+    const int h = tid >> 7, t = tid & 127;             // task = (j, j2)
+    if (h) phase_fwd1_split<true, 1>(t, acc, w, twd, rot); else phase_fwd1_split<true, 0>(t, acc, w, twd, rot);
+}
+NB_HD void pair_fwd2(int tid, u64 *w)
+{
+    const int h = tid >> 7, t = tid & 127;
+    const int g = t >> 5, p = (t >> 4) & 1, row = t & 15;          // g is warp-uniform
+    if (h) phase_fwd2_split<1>(p, row, g, w); else phase_fwd2_split<0>(p, row, g, w);
+}
+NB_HD void pair_fwd3_load(int tid, const u64 *w, u64 *v)
+{
+    const int t = tid & 127;
+    phase_fwd3_split_load(t >> 6, (t >> 2) & 15, t & 3, w, v);
+}
+NB_HD void pair_fwd3_finish(int tid, u64 *w, const u64 *v)
+{
+    const int h = tid >> 7, t = tid & 127;
+    if (h) phase_fwd3_split_finish<1>(t >> 6, (t >> 2) & 15, t & 3, w, v); else phase_fwd3_split_finish<0>(t >> 6, (t >> 2) & 15, t & 3, w, v);
+}
+// MAC of one point pair for ONE output polynomial mo: the two partial sums sum_j F_j * key[j][mo] (- correction).
+// key4: this CTA's four key planes [j * 2 + mo][row * 64 + stored column]; corr2: the two correction planes or null
+// (rank 1).  KEY_SHARED: the planes were staged in shared memory (the device kernel), else they are read in place.
+template <bool KEY_SHARED> NB_HD void mac_pair_point(int row, int q, const u64 *w_all, const u64 *key4, const u64 *corr2, int mo, u64 &o0, u64 &o1)
+{
+    const int pos = row * 64 + 2 * q;
+    u64 bk[2][2], cr[2] = {0, 0}, f[2][2];
+    static_for<0, 2>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        if constexpr (KEY_SHARED) ld2(key4 + (j * 2 + mo) * NTT_N + pos, bk[j][0], bk[j][1]);
+        else ld2_global(key4 + (j * 2 + mo) * NTT_N + pos, bk[j][0], bk[j][1]);
+    });
+    if (corr2) {
+        if constexpr (KEY_SHARED) ld2(corr2 + mo * NTT_N + pos, cr[0], cr[1]);
+        else ld2_global(corr2 + mo * NTT_N + pos, cr[0], cr[1]);
+    }
+    const u64 *w = w_all + row * ROW_STRIDE + 2 * q;
+    ld2(w, f[0][0], f[0][1]);
+    ld2(w + POLY_STRIDE, f[1][0], f[1][1]);
+    const u64 fa0[2] = {f[0][0], f[1][0]}, ba0[2] = {bk[0][0], bk[1][0]};
+    const u64 fa1[2] = {f[0][1], f[1][1]}, ba1[2] = {bk[0][1], bk[1][1]};
+    o0 = ff_dot2_sub_nc(fa0, ba0, cr[0]);
+    o1 = ff_dot2_sub_nc(fa1, ba1, cr[1]);
+#if NB_LAZY_CANON
+    if (canon_needed(umax32(hi32(o0), hi32(o1))))
+#endif
+    {
+        o0 = ff_canon_almost(o0);
+        o1 = ff_canon_almost(o1);
+    }
+}
+// The whole MAC of a thread: first the partial sums for the PEER's output polynomial (mo = 1 - rank), handed to
+// send(offset, x, y) -- a store at u64 offset `offset` of the peer's work polynomials: distributed shared memory on the
+// device, the other CTA's array in the host emulation -- so that they travel while this thread computes the partial sums
+// it keeps (mo = rank, into W[par], over the digit transform it has just read).
+template <bool KEY_SHARED, class Send>
+NB_HD void pair_mac(int tid, u64 *w, Send send, const u64 *key4, const u64 *corr2, int rank, int par)
+{
+    const int q = tid & 31;
+    for (int row = tid >> 5; row < 16; row += PAIR_THREADS / 32) {
+        u64 o0, o1;
+        mac_pair_point<KEY_SHARED>(row, q, w, key4, corr2, 1 - rank, o0, o1);
+        send((par + 2) * POLY_STRIDE + row * ROW_STRIDE + 2 * q, o0, o1);
+    }
+    for (int row = tid >> 5; row < 16; row += PAIR_THREADS / 32) {
+        u64 o0, o1;
+        mac_pair_point<KEY_SHARED>(row, q, w, key4, corr2, rank, o0, o1);
+        st2(w + par * POLY_STRIDE + row * ROW_STRIDE + 2 * q, o0, o1);
+    }
+}
+// key planes a CTA of the pair needs per step: its four (j, mo) planes, rank 0 also the two correction planes
+constexpr int PAIR_KEY_PLANES = 6;
+constexpr int PAIR_EXCHANGE_BYTES = NTT_N * (int)sizeof(u64);       // what a CTA receives per step
+// inverse phases: tid < PAIR_INV_WORKERS; task t = (row, u) / (g, row) / j2 of output polynomial W[par]
+NB_HD void pair_inv3_a(int tid, u64 *w, int par)
+{
+    const int h = tid >> 6, t = tid & 63;
+    if (h) phase_inv3_split_a<1, true>(par, t >> 2, t & 3, w); else phase_inv3_split_a<0, true>(par, t >> 2, t & 3, w);
+}
+NB_HD void pair_inv3_b(int tid, u64 *w, int par)
+{
+    const int h = tid >> 6, t = tid & 63;
+    if (h) phase_inv3_split_b<1>(par, t >> 2, t & 3, w); else phase_inv3_split_b<0>(par, t >> 2, t & 3, w);
+}
+NB_HD void pair_inv2(int tid, u64 *w, int par)
+{
+    // 16 tasks per g: two values of g per warp, the twiddle switch of phase_inv2_split runs twice (the only
+    // divergent piece of the shape: 6 shifts per thread)
+    const int h = tid >> 6, t = tid & 63;
+    if (h) phase_inv2_split<1>(par, t & 15, t >> 4, w); else phase_inv2_split<0>(par, t & 15, t >> 4, w);
+}
+NB_HD void pair_inv1_a(int tid, u64 *w, const u64 *twd_inv, int par)
+{
+    const int h = tid >> 6, t = tid & 63;
+    if (h) phase_inv1_split_a<1>(par * 64 + t, w, twd_inv); else phase_inv1_split_a<0>(par * 64 + t, w, twd_inv);
+}
+NB_HD void pair_inv1_b(int tid, i32 *acc, const u64 *w, int par)
+{
+    const int h = tid >> 6, t = tid & 63;
+    if (h) phase_inv1_split_b<true, 1>(par * 64 + t, acc, w, 0); else phase_inv1_split_b<true, 0>(par * 64 + t, acc, w, 0);
 }
 
 // ---- inv1: task = (ct, mo, j2): reads W[ct*4+mo], writes ACC[ct][mo] --------------------------------

@@ -18,6 +18,8 @@ struct nb_ctx {
     int sm_count;
     size_t wide_max;                     // largest batch launched in the wide (1 ciphertext / 256 threads) shape
     size_t wide2_max;                    // largest batch launched in the wide2 (1 ciphertext / 512 threads / SM) shape
+    size_t pair_max;                     // largest batch launched in the pair shape (1 ciphertext / cluster of 2 CTAs on 2 SMs)
+    int pair_async;                      // pair shape: exchange by st.async + mbarrier (1) or plain stores + barrier.cluster (0)
     int max_chunks;                      // upper bound on the chunks a chain is cut into (1 = no time slicing)
     unsigned *d_sched;                   // work-queue state of the fused bootstrap (kernels.cuh: BlindRotateArgs)
     size_t sched_words;
@@ -126,6 +128,10 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
                                            (int)br_smem_bytes<BrWide>()), "cudaFuncSetAttribute(blind_rotate wide)"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_kernel<BrWide2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)br_smem_bytes<BrWide2>()), "cudaFuncSetAttribute(blind_rotate wide2)"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)BR_PAIR_SMEM_BYTES), "cudaFuncSetAttribute(blind_rotate pair)"));
+    NB_TRY(check(ctx, cudaFuncSetAttribute(blind_rotate_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)BR_PAIR_SMEM_BYTES), "cudaFuncSetAttribute(blind_rotate pair)"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)KS_SMEM_BYTES), "cudaFuncSetAttribute(keyswitch)"));
     {   // batches that fit one wave of wide CTAs (one ciphertext on 256 threads) take the low-latency shape
@@ -137,6 +143,34 @@ int nb_ctx_create(int device, void *stream, nb_ctx **out)
         // measured crossover against the 256-thread shape between 200 and 296 ciphertexts, profiles/r2_variants.md)
         e = getenv("NUFHE_B200_WIDE2_MAX");
         ctx->wide2_max = e ? (size_t)atoll(e) : (size_t)ctx->sm_count * 3 / 2;
+        // up to one cluster of two SMs per ciphertext: the pair shape, while all clusters are resident at once (the
+        // driver knows how many pairs of SMs it can form)
+        e = getenv("NUFHE_B200_PAIR_ASYNC");
+        ctx->pair_async = e ? atoi(e) : 1;
+        e = getenv("NUFHE_B200_PAIR_MAX");
+        if (e) {
+            ctx->pair_max = (size_t)atoll(e);
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.gridDim = dim3(2 * (unsigned)ctx->sm_count); cfg.blockDim = dim3(PAIR_THREADS);
+            cfg.dynamicSmemBytes = BR_PAIR_SMEM_BYTES; cfg.attrs = &attr; cfg.numAttrs = 1;
+            int clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&clusters, blind_rotate_pair_kernel<true>, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                clusters = 0;
+            }
+            // measured (profiles/r2_variants.md section 7): 3.0 ms against 4.0 ms up to 24 ciphertexts, 3.45 at 48, and
+            // slower than the 512-thread shape at 64 (4.13 against 3.98) -- the more SMs of a GPC run, the less a shape
+            // with 8 warps per SM hides; the crossover is near 3/8 ciphertexts per SM
+            const size_t cap = (size_t)ctx->sm_count * 3 / 8;
+            ctx->pair_max = clusters > 0 ? ((size_t)clusters < cap ? (size_t)clusters : cap) : 0;
+        }
+        if (getenv("NUFHE_B200_VERBOSE"))
+            fprintf(stderr, "nufhe_b200: device %d, %d SMs; fused-kernel shapes by batch: pair <= %zu, wide2 <= %zu, wide <= %zu\n",
+                    ctx->device, ctx->sm_count, ctx->pair_max, ctx->wide2_max, ctx->wide_max);
     }
     NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_I32_BYTES)), "attr"));
     NB_TRY(check(ctx, cudaFuncSetAttribute(ntt_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_RAW_U64_BYTES)), "attr"));
@@ -334,6 +368,13 @@ template <class Cfg> static int launch_br_cfg(nb_ctx *ctx, BlindRotateArgs &p)
 // shortest step) while the batch fits one wave of them, else 2 ciphertexts per CTA (highest throughput).
 static int launch_br(nb_ctx *ctx, BlindRotateArgs &p)
 {
+    if (!p.plain && p.n > 0 && p.batch <= ctx->pair_max) {
+        p.sched = nullptr; p.state = nullptr; p.chains = (unsigned)p.batch; p.chunks = 1; p.steps_per_chunk = p.n;
+        p.sm_count = ctx->sm_count; p.stagger_cycles = 0;
+        if (ctx->pair_async) blind_rotate_pair_kernel<true><<<(unsigned)(2 * p.batch), PAIR_THREADS, BR_PAIR_SMEM_BYTES, ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);
+        else blind_rotate_pair_kernel<false><<<(unsigned)(2 * p.batch), PAIR_THREADS, BR_PAIR_SMEM_BYTES, ctx->stream>>>(p, ctx->d_ph_fwd, ctx->d_ph_inv);
+        return NB_OK;
+    }
     if (p.batch <= ctx->wide2_max) return launch_br_cfg<BrWide2>(ctx, p);
     if (p.batch <= ctx->wide_max) return launch_br_cfg<BrWide>(ctx, p);
     return launch_br_cfg<BrDefault>(ctx, p);

@@ -320,6 +320,20 @@ NB_HD u64 ff_dot4_sub_nc(const u64 *a, const u64 *b, u64 c)
 #endif
 }
 
+// two-term version for the pair shape (br_phases.cuh: every CTA of a pair multiplies its own two digit polynomials):
+// a0*b0 + a1*b1 - c as a residue in [0, 2^64) on the device, c canonical (0 allowed)
+NB_HD u64 ff_dot2_sub_nc(const u64 *a, const u64 *b, u64 c)
+{
+#if defined(__CUDA_ARCH__)
+    u32 c0, c1, c2, c3, c4 = 0;
+    mul128(a[0], b[0], c0, c1, c2, c3);
+    mac128(a[1], b[1], c0, c1, c2, c3, c4);
+    return ff_sub(ff_sub(ff_reduce_limbs_nc(c0, c1, c2, c3), (u64)c4 << 32), c);
+#else
+    return ff_sub(ff_add(ff_mul(a[0], b[0]), ff_mul(a[1], b[1])), c);
+#endif
+}
+
 // u * 2^(6*J1) for a small unsigned u < 2^10 (gadget digit + 512): the twist of the inner 16-point
 // transform without a general shift.  Result canonical.
 template <int J1> NB_HD u64 ff_twist_small(u32 u)

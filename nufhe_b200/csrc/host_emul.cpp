@@ -85,6 +85,8 @@ int emul_phase_ct(void) { return BR2_CT; }
 
 }  // extern "C"
 
+static void prepare_bk_row(const u64 *bk_ref_row, const PhaseTables &T, std::vector<u64> &bk);
+
 template <class Cfg> static void phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct)
 {
     static PhaseTables T;
@@ -94,17 +96,7 @@ template <class Cfg> static void phase_step(i32 *acc_io, const u64 *bk_ref_row, 
     for (int c = 0; c < nct; c++) memcpy(&acc[c * 2 * NTT_N], acc_io + c * 2 * NTT_N, sizeof(i32) * 2 * NTT_N);
     int rots[4] = {0, 0, 0, 0};
     if (rot) for (int c = 0; c < nct; c++) rots[c] = rot[c];
-    // bk_prepare: internal [m][row*64 + scol] plain
-    for (int pos = 0; pos < NTT_N; pos++) {
-        const int k = w_natural_index(pos >> 6, pos & 63);
-        u64 sum[2] = {0, 0};
-        for (int m = 0; m < 8; m++) {
-            u64 x = ff_mul(ff_canon(bk_ref_row[m * NTT_N + k]), FF_RINV);
-            bk[m * NTT_N + pos] = x;
-            sum[m & 1] = ff_add(sum[m & 1], x);
-        }
-        for (int mo = 0; mo < 2; mo++) bk[(8 + mo) * NTT_N + pos] = ff_mul(sum[mo], T.ones512[k]);
-    }
+    prepare_bk_row(bk_ref_row, T, bk);
     constexpr int TH = Cfg::THREADS;
     if constexpr (Cfg::SPLIT_FWD) {
         using Tasks = BrCfg<Cfg::CT, 256 * Cfg::CT>;
@@ -157,7 +149,62 @@ template <class Cfg> static void phase_step(i32 *acc_io, const u64 *bk_ref_row, 
     for (int c = 0; c < nct; c++) memcpy(acc_io + c * 2 * NTT_N, &acc[c * 2 * NTT_N], sizeof(i32) * 2 * NTT_N);
 }
 
+// the engine layout of one reference key row (kernels.cuh: bk_prepare_kernel)
+static void prepare_bk_row(const u64 *bk_ref_row, const PhaseTables &T, std::vector<u64> &bk)
+{
+    bk.assign(BK_ROW_U64, 0);
+    for (int pos = 0; pos < NTT_N; pos++) {
+        const int k = w_natural_index(pos >> 6, pos & 63);
+        u64 sum[2] = {0, 0};
+        for (int m = 0; m < 8; m++) {
+            u64 x = ff_mul(ff_canon(bk_ref_row[m * NTT_N + k]), FF_RINV);
+            bk[m * NTT_N + pos] = x;
+            sum[m & 1] = ff_add(sum[m & 1], x);
+        }
+        for (int mo = 0; mo < 2; mo++) bk[(8 + mo) * NTT_N + pos] = ff_mul(sum[mo], T.ones512[k]);
+    }
+}
+
+// `steps` consecutive CMux steps of the pair shape (kernels.cuh: blind_rotate_pair_kernel) with the same key row: two
+// "CTAs", each with its own work polynomials and accumulator polynomial, every barrier-separated sub-phase run for both
+// before the next one starts; the remote stores of the MAC go straight into the other CTA's array.  Several steps in a
+// row exercise both parities of the exchange area and what one step leaves behind for the next.
+static void pair_steps(i32 *acc_io, const u64 *bk_ref_row, const int *rots, int steps)
+{
+    static PhaseTables T;
+    std::vector<u64> bk;
+    prepare_bk_row(bk_ref_row, T, bk);
+    std::vector<u64> w[2] = {std::vector<u64>(PAIR_POLYS * POLY_STRIDE, 0x1234567887654321ull), std::vector<u64>(PAIR_POLYS * POLY_STRIDE, 0x0fedcba987654321ull)};
+    i32 *acc[2] = {acc_io, acc_io + NTT_N};
+    auto both = [&](int threads, auto fn) { for (int rank = 0; rank < 2; rank++) for (int tid = 0; tid < threads; tid++) fn(rank, tid); };
+    for (int i = 0; i < steps; i++) {
+        const int par = i & 1;
+        const int *rot = rots + i;
+        both(PAIR_THREADS, [&](int r, int tid) { pair_fwd1(tid, acc[r], w[r].data(), T.fwd.data(), rot); });
+        both(PAIR_THREADS, [&](int r, int tid) { pair_fwd2(tid, w[r].data()); });
+        std::vector<u64> held((size_t)2 * PAIR_THREADS * 16);
+        both(PAIR_THREADS, [&](int r, int tid) { pair_fwd3_load(tid, w[r].data(), &held[((size_t)r * PAIR_THREADS + tid) * 16]); });
+        both(PAIR_THREADS, [&](int r, int tid) { pair_fwd3_finish(tid, w[r].data(), &held[((size_t)r * PAIR_THREADS + tid) * 16]); });
+        both(PAIR_THREADS, [&](int r, int tid) {
+            u64 *peer = w[r ^ 1].data();
+            pair_mac<false>(tid, w[r].data(), [peer](int off, u64 x, u64 y) { peer[off] = x; peer[off + 1] = y; },
+                            bk.data() + r * 4 * NTT_N, r == 0 ? bk.data() + 8 * NTT_N : nullptr, r, par);
+        });
+        both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv3_a(tid, w[r].data(), par); });
+        both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv3_b(tid, w[r].data(), par); });
+        both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv2(tid, w[r].data(), par); });
+        both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv1_a(tid, w[r].data(), T.inv.data(), par); });
+        both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv1_b(tid, acc[r], w[r].data(), par); });
+    }
+}
+
 extern "C" {
+
+// the pair shape: `steps` CMux steps with rotation amounts rots[0 .. steps), all with the same key row
+void emul_phase_steps_pair(i32 *acc_io, const u64 *bk_ref_row, const int *rots, int steps)
+{
+    pair_steps(acc_io, bk_ref_row, rots, steps);
+}
 
 void emul_phase_step(i32 *acc_io, const u64 *bk_ref_row, const int *rot, int nct)
 {

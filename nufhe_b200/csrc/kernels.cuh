@@ -270,7 +270,7 @@ NB_HD i32 modswitch_2n(i32 x) { return (i32)(((u32)x + (1u << 20)) >> 21); }
 template <class Cfg> constexpr size_t br_smem_bytes()
 {
     return (size_t)Cfg::CT * 2 * NTT_N * sizeof(i32) + (size_t)Cfg::POLYS * POLY_STRIDE * sizeof(u64) +
-           (Cfg::TWD_GLOBAL ? 0 : 2 * NTT_N * sizeof(u64)) + 64;
+           (Cfg::TWD_GLOBAL ? 0 : 2 * NTT_N * sizeof(u64)) + 64 + (Cfg::STAGE_KEY ? BK_ROW_U64 * sizeof(u64) : 0);
 }
 constexpr size_t BR2_SMEM_BYTES = br_smem_bytes<BrDefault>();
 
@@ -308,7 +308,8 @@ struct Br2Smem {
     u64 *w;        // [16][POLY_STRIDE]
     u64 *twd_fwd;  // [16][64]
     u64 *twd_inv;
-    int *rot;      // [2][CT]
+    int *rot;      // [2][CT], 64 bytes
+    u64 *key;      // Cfg::STAGE_KEY: the key row of the current step, [BK_PLANES][1024]
 };
 
 template <class Cfg> NB_D Br2Smem br2_carve(unsigned char *raw)
@@ -319,6 +320,7 @@ template <class Cfg> NB_D Br2Smem br2_carve(unsigned char *raw)
     s.twd_inv = s.twd_fwd + (Cfg::TWD_GLOBAL ? 0 : NTT_N);
     s.acc = reinterpret_cast<i32 *>(s.twd_inv + (Cfg::TWD_GLOBAL ? 0 : NTT_N));
     s.rot = reinterpret_cast<int *>(s.acc + Cfg::CT * 2 * NTT_N);
+    s.key = reinterpret_cast<u64 *>(reinterpret_cast<unsigned char *>(s.rot) + 64);
     return s;
 }
 
@@ -336,8 +338,34 @@ NB_D int br2_rotation(const BlindRotateArgs &p, size_t c, int i)
     return modswitch_2n((i32)xa);
 }
 
+// coefficient x of polynomial mi of ciphertext c's accumulator before the first step
+NB_D i32 br2_initial_acc(const BlindRotateArgs &p, size_t c, int mi, int x)
+{
+    if (p.accum) return p.accum[(c * 2 + mi) * NTT_N + x];
+    if (mi == 0) return 0;
+    // ACC = (0, X^(2N - barb) * [mu, ..., mu])   (bootstrap.py:177-182, 224)
+    u32 xb;
+    if (p.job_batch && c >= p.job_batch) {
+        const size_t d = c - p.job_batch;
+        xb = (u32)p.j2_c + (u32)p.j2_s1 * (u32)p.j2_in1_b[d] + (p.j2_in2_b ? (u32)p.j2_s2 * (u32)p.j2_in2_b[d] : 0u);
+    } else {
+        xb = (u32)p.c + (u32)p.s1 * (u32)p.in1_b[c] + (p.in2_b ? (u32)p.s2 * (u32)p.in2_b[c] : 0u);
+    }
+    const int q = 2 * NTT_N - modswitch_2n((i32)xb);
+    if (q < NTT_N) return x < q ? (i32)(0u - (u32)p.mu) : p.mu;
+    return x < q - NTT_N ? p.mu : (i32)(0u - (u32)p.mu);
+}
+
+// 16-byte cp.async requests for one key row, spread over `nthreads` threads (t = 0 .. nthreads - 1); one commit group
+NB_D void br2_stage_key(u64 *key, const u64 *__restrict__ bk_row, int t, int nthreads)
+{
+    for (int x = t; x < BK_ROW_U64 / 2; x += nthreads) cp_async16(key + 2 * x, bk_row + 2 * x);
+    cp_async_commit();
+}
+
+// next_bk_row (Cfg::STAGE_KEY): the key row of the following step, or null
 template <bool ROTATE, class Cfg>
-NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *rot, int tid)
+NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *rot, int tid, const u64 *__restrict__ next_bk_row = nullptr)
 {
     // forward transforms of the digit polynomials (CT ciphertexts x 2 polynomials x 2 digits)
     if constexpr (Cfg::SPLIT_FWD) {
@@ -370,7 +398,8 @@ NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *
         __syncthreads();
     }
     // multiply-accumulate with the key row (tgsw_gpu.py:58-107); each key element is fetched once per CTA
-    phase_mac<Cfg>(tid, s.w, bk_row);
+    if constexpr (Cfg::STAGE_KEY) phase_mac<Cfg, true>(tid, s.w, s.key);
+    else phase_mac<Cfg>(tid, s.w, bk_row);
     __syncthreads();
     // inverse transforms of the output polynomials
     if constexpr (Cfg::SPLIT_INV) {
@@ -395,6 +424,11 @@ NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *
             if (h) phase_inv1_split_a<1>(t, s.w, s.twd_inv); else phase_inv1_split_a<0>(t, s.w, s.twd_inv);
             sync_workers();
             if (h) phase_inv1_split_b<ROTATE, 1>(t, s.acc, s.w); else phase_inv1_split_b<ROTATE, 0>(t, s.acc, s.w);
+        } else if constexpr (Cfg::STAGE_KEY) {
+            if (next_bk_row) {
+                br2_stage_key(s.key, next_bk_row, tid - 2 * Cfg::INV_TASKS, Cfg::THREADS - 2 * Cfg::INV_TASKS);
+                cp_async_wait<0>();                            // landed before this thread reaches the barrier that ends the step
+            }
         }
     } else {
         // (threads beyond Cfg::INV_TASKS idle: whole warps)
@@ -488,25 +522,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_k
             // accumulator initialisation: CT x 2 polynomials x 1024 coefficients
             for (int e = tid; e < ACC_WORDS; e += Cfg::THREADS) {
                 const int slot = e >> 11, mi = (e >> 10) & 1, x = e & (NTT_N - 1);
-                const size_t c = ct_of(slot);
-                i32 val;
-                if (p.accum) {
-                    val = p.accum[(c * 2 + mi) * NTT_N + x];
-                } else {
-                    // ACC = (0, X^(2N - barb) * [mu, ..., mu])   (bootstrap.py:177-182, 224)
-                    u32 xb;
-                    if (p.job_batch && c >= p.job_batch) {
-                        const size_t d = c - p.job_batch;
-                        xb = (u32)p.j2_c + (u32)p.j2_s1 * (u32)p.j2_in1_b[d] + (p.j2_in2_b ? (u32)p.j2_s2 * (u32)p.j2_in2_b[d] : 0u);
-                    } else {
-                        xb = (u32)p.c + (u32)p.s1 * (u32)p.in1_b[c] + (p.in2_b ? (u32)p.s2 * (u32)p.in2_b[c] : 0u);
-                    }
-                    int q = 2 * NTT_N - modswitch_2n((i32)xb);
-                    if (q < NTT_N) val = x < q ? (i32)(0u - (u32)p.mu) : p.mu;
-                    else val = x < q - NTT_N ? p.mu : (i32)(0u - (u32)p.mu);
-                    if (mi == 0) val = 0;
-                }
-                s.acc[e] = val;
+                s.acc[e] = br2_initial_acc(p, ct_of(slot), mi, x);
             }
         } else {
             // resume a parked chain: its queue entry was published after the accumulators (release / acquire above)
@@ -514,6 +530,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_k
             for (int e = tid; e < ACC_WORDS / 4; e += Cfg::THREADS) reinterpret_cast<int4 *>(s.acc)[e] = __ldcg(src + e);
         }
 
+        if constexpr (Cfg::STAGE_KEY) {
+            // first key row of this item (the rows after it are staged inside the steps)
+            br2_stage_key(s.key, p.bk + (size_t)(p.plain ? 0 : step0) * BK_ROW_U64, tid, Cfg::THREADS);
+            cp_async_wait<0>();
+        }
         if (p.plain) {
             __syncthreads();
             br2_step<false, Cfg>(s, p.bk, s.rot, tid);
@@ -524,7 +545,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_k
             for (int i = step0; i < step1; i++) {
                 int next = 0;
                 if (tid < Cfg::CT && i + 1 < step1) next = br2_rotation(p, ct_of(tid), i + 1);
-                br2_step<true, Cfg>(s, p.bk + (size_t)i * BK_ROW_U64, s.rot + (i & 1) * Cfg::CT, tid);
+                br2_step<true, Cfg>(s, p.bk + (size_t)i * BK_ROW_U64, s.rot + (i & 1) * Cfg::CT, tid,
+                                    i + 1 < step1 ? p.bk + (size_t)(i + 1) * BK_ROW_U64 : nullptr);
                 if (tid < Cfg::CT) s.rot[((i + 1) & 1) * Cfg::CT + tid] = next;
                 __syncthreads();
             }
@@ -556,6 +578,177 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_k
         }
         if (!p.sched) break;
     }
+}
+
+// ---- pair shape: one ciphertext per cluster of two CTAs (br_phases.cuh: "pair shape") -------------------------------
+// Lowest latency for batches of at most half the SM count.  No work queue (one cluster per ciphertext, one wave or
+// plain hardware queueing of clusters), blind rotation only (`plain` external products take the single-CTA shapes).
+// Dynamic shared memory is requested well above what the shape needs so that the two CTAs of a cluster can never
+// share an SM.
+constexpr size_t BR_PAIR_SMEM_USED = (size_t)PAIR_POLYS * POLY_STRIDE * sizeof(u64) + 2 * NTT_N * sizeof(u64) + NTT_N * sizeof(i32) + 64 +
+                                     (size_t)PAIR_KEY_PLANES * NTT_N * sizeof(u64);
+constexpr size_t BR_PAIR_SMEM_BYTES = 120 * 1024;
+static_assert(BR_PAIR_SMEM_USED <= BR_PAIR_SMEM_BYTES, "pair shape shared memory");
+
+NB_D unsigned cluster_cta_rank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// the address of `ptr` (this CTA's shared memory, generic) in CTA `rank` of the cluster
+NB_D u64 *cluster_map_shared(u64 *ptr, unsigned rank)
+{
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)ptr), "r"(rank));
+    return reinterpret_cast<u64 *>(out);
+}
+// the same for a 32-bit shared-window address (what st.async and mbarrier operands take)
+NB_D unsigned cluster_map_shared_u32(unsigned saddr, unsigned rank)
+{
+    unsigned out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(saddr), "r"(rank));
+    return out;
+}
+// cluster-wide barrier; orders this CTA's remote stores before the peer's loads after it
+NB_D void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+NB_D void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+NB_D void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+NB_D void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "NB_MBAR_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra NB_MBAR_WAIT;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 16 bytes into the peer's shared memory, completion counted on the peer's mbarrier
+NB_D void st_async_peer(unsigned raddr, u64 x, u64 y, unsigned rbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr), "l"(x), "l"(y), "r"(rbar) : "memory");
+}
+
+// ASYNC: the partial sums travel as st.async stores that count their bytes on an mbarrier of the receiving CTA, one
+// per step parity, which the receiver arms at the top of the step and waits for after its own MAC: no cluster-wide
+// barrier in the step loop.  Flow control is the data dependence itself (br_phases.cuh: pair shape).
+// !ASYNC: plain remote stores and one barrier.cluster per step -- ptxas implements its release / acquire with a
+// GPU-scope memory barrier and an L1 invalidation, which is why the other variant exists; kept as the reference
+// implementation (NUFHE_B200_PAIR_ASYNC=0).
+template <bool ASYNC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+blind_rotate_pair_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g, const u64 *__restrict__ twd_inv_g)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    u64 *w = reinterpret_cast<u64 *>(smem_raw);
+    u64 *twd_fwd = w + PAIR_POLYS * POLY_STRIDE, *twd_inv = twd_fwd + NTT_N;
+    i32 *acc = reinterpret_cast<i32 *>(twd_inv + NTT_N);       // this CTA's accumulator polynomial
+    int *rot = reinterpret_cast<int *>(acc + NTT_N);           // [2], 64 bytes reserved
+    // this CTA's key planes of the current step: [j * 2 + mo] and, rank 0 only, the two correction planes
+    u64 *key = reinterpret_cast<u64 *>(reinterpret_cast<unsigned char *>(rot) + 64);
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_cta_rank();
+    const size_t c = blockIdx.x >> 1;                          // grid = 2 x batch
+    // The key row of step i + 1 is staged by the warps that have no inverse work while the others run the inverse
+    // phases of step i (cp.async, 16 bytes per request): the MAC then reads shared memory instead of waiting for the L2,
+    // whose latency a step of 8 warps cannot hide -- and which every CTA of the launch asks for the same lines at the
+    // same time.
+    const int key_planes = rank == 0 ? PAIR_KEY_PLANES : 4;
+    auto stage_key = [&](int step, int t, int nthreads) {
+        const u64 *row = p.bk + (size_t)step * BK_ROW_U64;
+        for (int x = t; x < key_planes * (NTT_N / 2); x += nthreads) {
+            const int pl = x >> 9, e = (x & 511) * 2;
+            const int src = pl < 4 ? rank * 4 + pl : 4 + pl;      // planes 8, 9: corrections
+            cp_async16(key + pl * NTT_N + e, row + (size_t)src * NTT_N + e);
+        }
+        cp_async_commit();
+    };
+    if (p.n > 0) stage_key(0, tid, PAIR_THREADS);
+    for (int i = tid; i < NTT_N; i += PAIR_THREADS) {
+        twd_fwd[i] = twd_fwd_g[i]; twd_inv[i] = twd_inv_g[i];
+        acc[i] = br2_initial_acc(p, c, rank, i);
+    }
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar);
+    if (tid == 0) {
+        rot[0] = br2_rotation(p, c, 0);
+        if (ASYNC) {
+            mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    u64 *w_peer = cluster_map_shared(w, (unsigned)(rank ^ 1));
+    const unsigned w_peer32 = cluster_map_shared_u32((unsigned)__cvta_generic_to_shared(w), (unsigned)(rank ^ 1));
+    const unsigned bar_peer = cluster_map_shared_u32(bar0, (unsigned)(rank ^ 1));
+    cp_async_wait<0>();
+    cluster_barrier();                                         // the peer is running, its barriers are initialised
+
+    const u64 *corr2 = rank == 0 ? key + 4 * NTT_N : nullptr;
+    for (int i = 0; i < p.n; i++) {
+        const int par = i & 1;
+        const int *r = rot + par;
+        int next = 0;
+        if (tid == 0) {
+            if (ASYNC) mbar_expect_tx(bar0 + 8 * par, PAIR_EXCHANGE_BYTES);
+            if (i + 1 < p.n) next = br2_rotation(p, c, i + 1);
+        }
+        pair_fwd1(tid, acc, w, twd_fwd, r);
+        __syncthreads();
+        pair_fwd2(tid, w);
+        __syncthreads();
+        {
+            u64 v[16];
+            pair_fwd3_load(tid, w, v);
+            __syncthreads();                                   // in place: all loads before any store
+            pair_fwd3_finish(tid, w, v);
+        }
+        __syncthreads();
+        if (ASYNC) {
+            const unsigned rb = bar_peer + 8 * par;
+            pair_mac<true>(tid, w, [=](int off, u64 x, u64 y) { st_async_peer(w_peer32 + 8u * (unsigned)off, x, y, rb); },
+                           key, corr2, rank, par);
+            __syncthreads();                                   // this CTA's own partial sums; the key planes are free
+        } else {
+            pair_mac<true>(tid, w, [=](int off, u64 x, u64 y) { st2(w_peer + off, x, y); }, key, corr2, rank, par);
+            cluster_barrier();
+        }
+        if (tid >= PAIR_INV_WORKERS) {
+            if (i + 1 < p.n) {
+                stage_key(i + 1, tid - PAIR_INV_WORKERS, PAIR_THREADS - PAIR_INV_WORKERS);
+                cp_async_wait<0>();                            // landed before this thread reaches the barrier that ends the step
+            }
+        } else {
+            auto sync_workers = [] { asm volatile("bar.sync 1, %0;" ::"n"(PAIR_INV_WORKERS) : "memory"); };
+            if (ASYNC) mbar_wait(bar0 + 8 * par, (unsigned)(i >> 1) & 1u);   // the peer's partial sums have landed
+            pair_inv3_a(tid, w, par);
+            sync_workers();
+            pair_inv3_b(tid, w, par);
+            sync_workers();
+            pair_inv2(tid, w, par);
+            sync_workers();
+            pair_inv1_a(tid, w, twd_inv, par);
+            sync_workers();
+            pair_inv1_b(tid, acc, w, par);
+        }
+        if (tid == 0) rot[par ^ 1] = next;
+        __syncthreads();
+    }
+
+    for (int x = tid; x < NTT_N; x += PAIR_THREADS) {
+        if (p.accum_out) p.accum_out[(c * 2 + rank) * NTT_N + x] = acc[x];
+        if (p.extract) {
+            // sample extraction (tlwe_gpu.mako:63-82; blind_rotate.mako:213-224): a from polynomial 0, b from polynomial 1
+            if (rank == 0) p.out_a[c * NTT_N + x] = x == 0 ? acc[0] : (i32)(0u - (u32)acc[NTT_N - x]);
+            else if (x == 0) p.out_b[c] = acc[0];
+        }
+    }
+    // nothing is in flight towards this CTA (it has waited for every exchange) and nothing it sent is unreceived
+    // while the peer still runs, but the peer's shared memory must outlive the stores addressed to it: both leave together
+    cluster_barrier();
 }
 
 // ---- the separate kernels of the reference's multi-kernel bootstrap (bootstrap.py:96-196) ---------------

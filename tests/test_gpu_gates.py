@@ -118,21 +118,25 @@ def test_full_size_batches_decrypt_to_truth_table(eng, keys, dev_keys, batch):
 
 
 def test_all_cta_shapes_give_the_same_bits(keys, monkeypatch):
-    """The fused kernel has three CTA shapes: 2 ciphertexts per 256 threads (throughput), 1 ciphertext per 256 threads
-    (inverse phases split over thread pairs) and 1 ciphertext per 512 threads (forward phases split as well; batches
-    up to one ciphertext per SM).  Force each shape for the same inputs, including a ragged batch and one larger than
-    a wave of the wide CTAs (time-sliced); all must equal the oracle and each other."""
+    """The fused kernel has four shapes: 2 ciphertexts per 256 threads (throughput), 1 ciphertext per 256 threads
+    (inverse phases split over thread pairs), 1 ciphertext per 512 threads (forward phases split as well; batches
+    up to 1.5 ciphertexts per SM) and 1 ciphertext per cluster of two 256-thread CTAs on two SMs (partial sums of the
+    MAC exchanged through distributed shared memory; batches up to half the SM count).  Force each shape for the same
+    inputs, including a ragged batch and one larger than a wave (time-sliced, or clusters queued by the hardware); all
+    must equal the oracle and each other."""
     from nufhe_b200.engine import Engine
     rng = G.rs(480)
-    shapes = {'default': ('0', '0'), 'wide': ('1000000', '0'), 'wide2': ('1000000', '1000000')}
+    shapes = {'default': ('0', '0', '0'), 'wide': ('1000000', '0', '0'), 'wide2': ('1000000', '1000000', '0'),
+              'pair': ('0', '0', '1000000')}
     for B in (1, 5, 301):
         bits_a, bits_b = rng.randint(0, 2, B).astype(bool), rng.randint(0, 2, B).astype(bool)
         a, b = keys.encrypt(bits_a), keys.encrypt(bits_b)
         want = O.gate_binary('nand', a, b, keys.bk, keys.ks) if B <= 5 else None
         outs = {}
-        for name, (wide_max, wide2_max) in shapes.items():
+        for name, (wide_max, wide2_max, pair_max) in shapes.items():
             monkeypatch.setenv('NUFHE_B200_WIDE_MAX', wide_max)
             monkeypatch.setenv('NUFHE_B200_WIDE2_MAX', wide2_max)
+            monkeypatch.setenv('NUFHE_B200_PAIR_MAX', pair_max)
             eng = Engine()
             dk = (eng.bk_prepare(eng.to_device(keys.bk)),
                   (eng.to_device(keys.ks_a), eng.to_device(keys.ks_b), eng.to_device(keys.ks_cv)))
@@ -141,7 +145,7 @@ def test_all_cta_shapes_give_the_same_bits(keys, monkeypatch):
             if want is not None:
                 assert (out[0] == want[0]).all() and (out[1] == want[1]).all(), (B, name)
             assert (keys.decrypt(out) == ~(bits_a & bits_b)).all()
-        for name in ('wide', 'wide2'):
+        for name in ('wide', 'wide2', 'pair'):
             for x, y in zip(outs['default'], outs[name]):
                 assert (x[0] == y[0]).all() and (x[1] == y[1]).all(), (B, name)
 
@@ -272,7 +276,7 @@ print('rare path ok')
 '''
 
 
-@pytest.mark.parametrize('wide_max', ['0', '1000000', 'wide2'])
+@pytest.mark.parametrize('wide_max', ['0', '1000000', 'wide2', 'pair'])
 def test_canonicalisation_rare_path_forced(wide_max):
     """NUFHE_B200_FORCE_RARE_PATH=1 lowers the trigger of the deferred canonicalisation so that EVERY task of fwd1,
     inv1 and the MAC runs its fix-up code (normally 2^-32 per element); results must not change.  Runs in a fresh
@@ -282,8 +286,9 @@ def test_canonicalisation_rare_path_forced(wide_max):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, NUFHE_B200_FORCE_RARE_PATH='1')
+    env['NUFHE_B200_PAIR_MAX'] = '1000000' if wide_max == 'pair' else '0'
     env.update({'NUFHE_B200_WIDE_MAX': '1000000', 'NUFHE_B200_WIDE2_MAX': '1000000'} if wide_max == 'wide2' else
-               {'NUFHE_B200_WIDE_MAX': wide_max, 'NUFHE_B200_WIDE2_MAX': '0'})
+               {'NUFHE_B200_WIDE_MAX': '0' if wide_max == 'pair' else wide_max, 'NUFHE_B200_WIDE2_MAX': '0'})
     r = subprocess.run([sys.executable, '-c', _RARE_PATH_SCRIPT % {'root': root}], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and 'rare path ok' in r.stdout, r.stdout + r.stderr

@@ -262,6 +262,21 @@ def test_phase_structured_step_matches_oracle(emul):
             assert (a == O.blind_rotate(acc, bk[0:1], rot.reshape(1, 1))).all()
 
 
+def test_pair_shape_steps_match_oracle(emul):
+    """The pair shape (one ciphertext on a cluster of two CTAs, csrc/br_phases.cuh) on the host: two emulated CTAs,
+    the partial sums of the MAC exchanged through each other's work polynomials.  Several consecutive steps cover both
+    parities of the exchange area and whatever one step leaves behind in shared memory for the next."""
+    rng = G.rs(78)
+    bk = G.ff_numbers(rng, (2, 2, 2, 2, 1024))
+    for rots in ([0], [1024], [5, 2047, 1023, 1], [2047, 0, 77]):
+        acc = G.torus32(rng, (1, 2, 1024))
+        a = acc.copy()
+        r = numpy.array(rots, numpy.int32)
+        emul.emul_phase_steps_pair(_p(a), _p(bk[0]), _p(r), ctypes.c_int(len(rots)))
+        rows = numpy.stack([bk[0]] * len(rots))
+        assert (a == O.blind_rotate(acc, rows, r.reshape(1, -1))).all()
+
+
 def test_uint_bit_helpers_roundtrip():
     from nufhe_b200.operators_integer import uintarray_to_bitarray, bitarray_to_uintarray
     xs = numpy.array([[0, 1, 255], [128, 77, 200]], numpy.uint8)

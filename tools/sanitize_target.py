@@ -44,8 +44,10 @@ ks_cv = torch.empty((16, 8, 4), dtype=torch.float32).cuda()
 eng.make_keyswitch_key(ks_a, ks_b, ks_cv, r32((16,), 0, 2), key, r32((16, 8, 3, 500)), r32((16, 8, 3)), 2, 1e-9)
 # the three CTA shapes of the fused kernel on the same small batch (the environment is read when an engine is created):
 # throughput, wide (split inverse phases, exchange through shared memory) and wide2 (split forward phases as well)
-for wide_max, wide2_max in (('0', '0'), ('1000000', '0'), ('1000000', '1000000')):
+# ... and the pair shape (a cluster of two CTAs per ciphertext, remote shared-memory stores)
+for wide_max, wide2_max, pair_max in (('0', '0', '0'), ('1000000', '0', '0'), ('1000000', '1000000', '0'), ('0', '0', '1000000')):
     os.environ['NUFHE_B200_WIDE_MAX'], os.environ['NUFHE_B200_WIDE2_MAX'] = wide_max, wide2_max
+    os.environ['NUFHE_B200_PAIR_MAX'] = pair_max
     e2 = Engine(0)
     e2.bootstrap_extract(x1, x2, 2**29, -1, -1, 2**29, bk)
     e2.blind_rotate(acc, bara, bk, return_accum=True)

@@ -54,14 +54,14 @@ for B in BATCHES:
                              'hbm_gbs_per_step_model': alg / ms / 1e6, 'hbm_frac': alg / ms / 1e6 / peak})
     print(out['gate_nand'][-1], flush=True)
     del x, y, dest
-for B in (4096,):
+for B in (() if os.environ.get('SWEEP_NO_MUX') else (4096,)):
     x, y, z = rand_ct(B), rand_ct(B), rand_ct(B)
     dest = vm.empty_ciphertext((B,))
     ms = time_ms(lambda: vm.gate_mux(x, y, z, dest=dest), 3)
     out['gate_mux'].append({'batch': B, 'ms': ms, 'ms_per_gate': ms / B, 'gates_per_s': B / ms * 1e3})
     print(out['gate_mux'][-1], flush=True)
     del x, y, z, dest
-for NT in (4096, 65536, 262144):
+for NT in (() if os.environ.get('SWEEP_NO_MUX') else (4096, 65536, 262144)):
     polys = torch.randint(-2**31, 2**31, (NT, 1024), generator=gen, dtype=torch.int64).to(torch.int32).to(thr.device)
     f = thr.ntt_forward_i32(polys)
     outbuf = torch.empty_like(f)
