@@ -734,20 +734,133 @@ template <class Cfg = BrDefault, bool KEY_SHARED = false> NB_HD void phase_mac(i
     for (int row = tid >> 5; row < 16; row += Cfg::THREADS / 32) phase_mac_row<Cfg::CT, KEY_SHARED>(row, tid & 31, w_all, bk_row);
 }
 
+// ---- quarter-split inverse phases (pair shape) ----------------------------------------------------------------------
+// Four threads (of different warps) per 16-element inverse task.  The 16-point decimation-in-time network is two layers
+// inside the blocks {4 B .. 4 B + 3} (a 4-point network, root 2^48) followed by two layers inside the residue classes
+// {R, R + 4, R + 8, R + 12} (pairs (R, R + 4) and (R + 8, R + 12) with twiddle 2^(-24 R), then (R, R + 8) with
+// 2^(-12 R) and (R + 4, R + 12) with 2^(-12 (R + 4))).  Quarter B runs the first two layers on its block and parks the
+// four values in work polynomial p + 2; after a CTA barrier quarter R reads the parked values of its residue class and
+// finishes those four outputs.  Same barrier count as the two-way split, about half of its instructions per thread.
+template <int E> NB_HD void dit_pair(u64 &a, u64 &b)       // one butterfly of dit_inlane with inverse twiddle 2^-E
+{
+    if constexpr (E > 0 && E < 96) {
+        const u64 x = a, t = ff_shl<96 - E>(b);
+        a = ff_sub(x, t);
+        b = ff_add(x, t);
+    } else {
+        const u64 x = a, t = ff_shl<(192 - E) % 192>(b);
+        a = ff_add(x, t);
+        b = ff_sub(x, t);
+    }
+}
+template <int R> NB_HD void dit16_quarter_b(u64 *x)       // x[m] = parked element R + 4 m, becomes output element R + 4 m
+{
+    dit_pair<24 * R>(x[0], x[1]);
+    dit_pair<24 * R>(x[2], x[3]);
+    dit_pair<12 * R>(x[0], x[2]);
+    dit_pair<12 * R + 48>(x[1], x[3]);
+}
+// inv3, first stage: task (p, row, u), logical columns 4 B .. 4 B + 3 of block u (pairs 2 B, 2 B + 1)
+template <int B, bool ADD_PARKED> NB_HD void phase_inv3_quarter_a(int p, int row, int u, u64 *w_all)
+{
+    const u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    u64 *x = w_all + (p + 2) * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[4];
+    static_for<0, 2>([&](auto PI) {
+        constexpr int pi = 2 * B + decltype(PI)::value;
+        constexpr int k = 2 * decltype(PI)::value;
+        ld2(w + 16 * u + 2 * ((pi ^ (2 * u)) & 7), v[k], v[k + 1]);
+        if constexpr (ADD_PARKED) {
+            u64 r0, r1;
+            ld2(x + 16 * u + 2 * ((pi ^ (2 * u)) & 7), r0, r1);
+            v[k] = ff_add(v[k], r0);
+            v[k + 1] = ff_add(v[k + 1], r1);
+        }
+    });
+    dit_inlane<2, 48, 0>(v);
+    static_for<0, 2>([&](auto PI) {
+        constexpr int pi = 2 * B + decltype(PI)::value;
+        st2(x + 16 * u + 2 * ((pi ^ (2 * u)) & 7), v[2 * decltype(PI)::value], v[2 * decltype(PI)::value + 1]);
+    });
+}
+// inv3, second stage: logical columns R, R + 4, R + 8, R + 12 of block u
+template <int R> NB_HD void phase_inv3_quarter_b(int p, int row, int u, u64 *w_all)
+{
+    u64 *w = w_all + p * POLY_STRIDE + row * ROW_STRIDE;
+    const u64 *x = w_all + (p + 2) * POLY_STRIDE + row * ROW_STRIDE;
+    u64 v[4];
+    static_for<0, 4>([&](auto M) {
+        constexpr int b = R + 4 * decltype(M)::value;
+        v[decltype(M)::value] = x[16 * u + 2 * (((b >> 1) ^ (2 * u)) & 7) + (b & 1)];
+    });
+    dit16_quarter_b<R>(v);
+    static_for<0, 4>([&](auto M) {
+        constexpr int b = R + 4 * decltype(M)::value;
+        w[16 * u + 2 * (((b >> 1) ^ (2 * u)) & 7) + (b & 1)] = v[decltype(M)::value];
+    });
+}
+// inv1, first stage: task = (polynomial pp, column j2); rows 4 B .. 4 B + 3 times the twiddles, 4-point network
+template <int B> NB_HD void phase_inv1_quarter_a(int task, u64 *w_all, const u64 *twd_inv)
+{
+    const int j2 = task & 63, pp = task >> 6;
+    const int p = (pp >> 1) * 4 + (pp & 1);
+    const int col = col_of(j2 >> 4, j2 & 15);
+    const u64 *w = w_all + p * POLY_STRIDE + col + 4 * B * ROW_STRIDE;
+    u64 *x = w_all + (p + 2) * POLY_STRIDE + col + 4 * B * ROW_STRIDE;
+    const u64 *twd = twd_inv + 4 * B * 64 + j2;
+    u64 v[4];
+    u32 hmax = 0;
+    static_for<0, 4>([&](auto R) {
+        constexpr int r = decltype(R)::value;
+#if NB_LAZY_CANON
+        v[r] = ff_mul_nc(w[r * ROW_STRIDE], twd[r * 64]);
+        hmax = umax32(hmax, hi32(v[r]));
+#else
+        v[r] = ff_mul(w[r * ROW_STRIDE], twd[r * 64]);
+#endif
+    });
+#if NB_LAZY_CANON
+    if (canon_needed(hmax)) {
+        static_for<0, 4>([&](auto R) { v[decltype(R)::value] = ff_canon_almost(v[decltype(R)::value]); });
+    }
+#endif
+    dit_inlane<2, 48, 0>(v);
+    static_for<0, 4>([&](auto R) { x[decltype(R)::value * ROW_STRIDE] = v[decltype(R)::value]; });
+}
+// inv1, second stage: outputs j1 = R + 4 m of column j2 into accumulator polynomial acc_poly
+template <int R> NB_HD void phase_inv1_quarter_b(int task, i32 *acc_all, const u64 *w_all, int acc_poly)
+{
+    const int j2 = task & 63, pp = task >> 6;
+    const u64 *x = w_all + ((pp >> 1) * 4 + (pp & 1) + 2) * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
+    u64 v[4];
+    static_for<0, 4>([&](auto M) { v[decltype(M)::value] = x[(R + 4 * decltype(M)::value) * ROW_STRIDE]; });
+    dit16_quarter_b<R>(v);
+    i32 *acc = acc_all + acc_poly * NTT_N;
+    static_for<0, 4>([&](auto M) {
+        constexpr int j1 = R + 4 * decltype(M)::value;
+        const int idx = 64 * j1 + j2;
+        if constexpr (j1 == 0) {
+            acc[idx] = (i32)((u32)acc[idx] + (u32)ff_to_i32(v[0]));
+        } else {
+            acc[idx] = (i32)((u32)acc[idx] - (u32)ff_to_i32(ff_shl<96 - 6 * j1>(v[decltype(M)::value])));
+        }
+    });
+}
+
 // ---- pair shape: one ciphertext on a cluster of two CTAs (two SMs), 256 threads each ---------------------------------
 // CTA `rank` (= mi) owns accumulator polynomial mi: it decomposes it into its two digit polynomials (W[0], W[1]),
 // transforms them (split forward phases, 128 tasks x 2 halves), and multiplies them with the four key planes
 // (mi, j, mo): two partial sums per point, one for each output polynomial.  The partial sum for its OWN output
 // polynomial (mo = rank) stays in W[par]; the other one goes into the peer's W[par + 2] through distributed shared
 // memory, par = step parity.  After one cluster barrier each CTA adds what it received to what it kept (fused into the
-// first inverse pass), runs the inverse transform of its output polynomial (split inverse phases on 128 of the 256
-// threads, W[par + 2] doubling as the exchange area like in the single-CTA shapes) and updates its accumulator polynomial:
+// first inverse pass), runs the inverse transform of its output polynomial (quarter-split inverse phases, four threads per
+// task, W[par + 2] doubling as the exchange area like in the single-CTA shapes) and updates its accumulator polynomial:
 // everything but the exchange of 8 KB per step and direction is local to a CTA.  Alternating par is what makes the
 // exchange safe without a second synchronisation per step: the peer's next remote stores (into W[(par ^ 1) + 2]) can
 // start while this CTA is still in the inverse phases of the current step (W[par], W[par + 2]); the stores after those
 // need this CTA's next partial sums first, which it sends after finishing the current step.
 // The correction plane of the unsigned digits (BK planes 8, 9) is subtracted by rank 0 alone.
-// The per-thread instruction stream is that of the 512-thread shape, but each SM carries 8 warps instead of 16.
+// The per-thread instruction stream is shorter than that of the 512-thread shape and each SM carries 8 warps, not 16.
 constexpr int PAIR_THREADS = 256;
 constexpr int PAIR_POLYS = 4;
 constexpr int PAIR_INV_WORKERS = 128;                 // threads with work in the inverse phases (64 tasks x 2 halves)
@@ -826,34 +939,33 @@ NB_HD void pair_mac(int tid, u64 *w, Send send, const u64 *key4, const u64 *corr
 // key planes a CTA of the pair needs per step: its four (j, mo) planes, rank 0 also the two correction planes
 constexpr int PAIR_KEY_PLANES = 6;
 constexpr int PAIR_EXCHANGE_BYTES = NTT_N * (int)sizeof(u64);       // what a CTA receives per step
-// inverse phases: tid < PAIR_INV_WORKERS; task t = (row, u) / (g, row) / j2 of output polynomial W[par]
-NB_HD void pair_inv3_a(int tid, u64 *w, int par)
+// inverse phases of output polynomial W[par].  inv3 and inv1: all 256 threads, four per task (quarter = tid / 64, whole
+// warps; task t = tid % 64 = (row, u) resp. j2).  inv2: the two-way split on tid < PAIR_INV_WORKERS, task t = (g, row) --
+// its four 4-point transforms per task are independent, and the other warps use the time to request the next key row.
+template <template <int> class F, class... A> NB_HD void pair_quarter_dispatch(int quarter, A... a)
 {
-    const int h = tid >> 6, t = tid & 63;
-    if (h) phase_inv3_split_a<1, true>(par, t >> 2, t & 3, w); else phase_inv3_split_a<0, true>(par, t >> 2, t & 3, w);
+    switch (quarter) {                                 // warp-uniform
+    case 0: F<0>::run(a...); break;
+    case 1: F<1>::run(a...); break;
+    case 2: F<2>::run(a...); break;
+    default: F<3>::run(a...); break;
+    }
 }
-NB_HD void pair_inv3_b(int tid, u64 *w, int par)
-{
-    const int h = tid >> 6, t = tid & 63;
-    if (h) phase_inv3_split_b<1>(par, t >> 2, t & 3, w); else phase_inv3_split_b<0>(par, t >> 2, t & 3, w);
-}
-NB_HD void pair_inv2(int tid, u64 *w, int par)
+template <int Q> struct PairInv3A { NB_HD static void run(int t, u64 *w, int par) { phase_inv3_quarter_a<Q, true>(par, t >> 2, t & 3, w); } };
+template <int Q> struct PairInv3B { NB_HD static void run(int t, u64 *w, int par) { phase_inv3_quarter_b<Q>(par, t >> 2, t & 3, w); } };
+template <int Q> struct PairInv1A { NB_HD static void run(int t, u64 *w, const u64 *twd_inv, int par) { phase_inv1_quarter_a<Q>(par * 64 + t, w, twd_inv); } };
+template <int Q> struct PairInv1B { NB_HD static void run(int t, i32 *acc, const u64 *w, int par) { phase_inv1_quarter_b<Q>(par * 64 + t, acc, w, 0); } };
+NB_HD void pair_inv3_a(int tid, u64 *w, int par) { pair_quarter_dispatch<PairInv3A>(tid >> 6, tid & 63, w, par); }
+NB_HD void pair_inv3_b(int tid, u64 *w, int par) { pair_quarter_dispatch<PairInv3B>(tid >> 6, tid & 63, w, par); }
+NB_HD void pair_inv2(int tid, u64 *w, int par)         // tid < PAIR_INV_WORKERS
 {
     // 16 tasks per g: two values of g per warp, the twiddle switch of phase_inv2_split runs twice (the only
     // divergent piece of the shape: 6 shifts per thread)
     const int h = tid >> 6, t = tid & 63;
     if (h) phase_inv2_split<1>(par, t & 15, t >> 4, w); else phase_inv2_split<0>(par, t & 15, t >> 4, w);
 }
-NB_HD void pair_inv1_a(int tid, u64 *w, const u64 *twd_inv, int par)
-{
-    const int h = tid >> 6, t = tid & 63;
-    if (h) phase_inv1_split_a<1>(par * 64 + t, w, twd_inv); else phase_inv1_split_a<0>(par * 64 + t, w, twd_inv);
-}
-NB_HD void pair_inv1_b(int tid, i32 *acc, const u64 *w, int par)
-{
-    const int h = tid >> 6, t = tid & 63;
-    if (h) phase_inv1_split_b<true, 1>(par * 64 + t, acc, w, 0); else phase_inv1_split_b<true, 0>(par * 64 + t, acc, w, 0);
-}
+NB_HD void pair_inv1_a(int tid, u64 *w, const u64 *twd_inv, int par) { pair_quarter_dispatch<PairInv1A>(tid >> 6, tid & 63, w, twd_inv, par); }
+NB_HD void pair_inv1_b(int tid, i32 *acc, const u64 *w, int par) { pair_quarter_dispatch<PairInv1B>(tid >> 6, tid & 63, acc, w, par); }
 
 // ---- inv1: task = (ct, mo, j2): reads W[ct*4+mo], writes ACC[ct][mo] --------------------------------
 // twd_inv: [row][j2] = psi^-(j2 (2 k1 + 1)) / 1024.  ACCUMULATE: acc += result, else acc = result.

@@ -190,11 +190,11 @@ static void pair_steps(i32 *acc_io, const u64 *bk_ref_row, const int *rots, int 
             pair_mac<false>(tid, w[r].data(), [peer](int off, u64 x, u64 y) { peer[off] = x; peer[off + 1] = y; },
                             bk.data() + r * 4 * NTT_N, r == 0 ? bk.data() + 8 * NTT_N : nullptr, r, par);
         });
-        both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv3_a(tid, w[r].data(), par); });
-        both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv3_b(tid, w[r].data(), par); });
+        both(PAIR_THREADS, [&](int r, int tid) { pair_inv3_a(tid, w[r].data(), par); });
+        both(PAIR_THREADS, [&](int r, int tid) { pair_inv3_b(tid, w[r].data(), par); });
         both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv2(tid, w[r].data(), par); });
-        both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv1_a(tid, w[r].data(), T.inv.data(), par); });
-        both(PAIR_INV_WORKERS, [&](int r, int tid) { pair_inv1_b(tid, acc[r], w[r].data(), par); });
+        both(PAIR_THREADS, [&](int r, int tid) { pair_inv1_a(tid, w[r].data(), T.inv.data(), par); });
+        both(PAIR_THREADS, [&](int r, int tid) { pair_inv1_b(tid, acc[r], w[r].data(), par); });
     }
 }
 

@@ -654,10 +654,10 @@ blind_rotate_pair_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g, c
     const int tid = threadIdx.x;
     const int rank = (int)cluster_cta_rank();
     const size_t c = blockIdx.x >> 1;                          // grid = 2 x batch
-    // The key row of step i + 1 is staged by the warps that have no inverse work while the others run the inverse
-    // phases of step i (cp.async, 16 bytes per request): the MAC then reads shared memory instead of waiting for the L2,
-    // whose latency a step of 8 warps cannot hide -- and which every CTA of the launch asks for the same lines at the
-    // same time.
+    // The key row of step i + 1 is requested (cp.async, 16 bytes per request) by the warps that have no work in the
+    // middle inverse pass of step i and lands during the last one: the MAC then reads shared memory instead of waiting
+    // for the L2, whose latency a step of 8 warps cannot hide -- and which every CTA of the launch asks for the same
+    // lines at the same time.
     const int key_planes = rank == 0 ? PAIR_KEY_PLANES : 4;
     auto stage_key = [&](int step, int t, int nthreads) {
         const u64 *row = p.bk + (size_t)step * BK_ROW_U64;
@@ -716,24 +716,18 @@ blind_rotate_pair_kernel(BlindRotateArgs p, const u64 *__restrict__ twd_fwd_g, c
             pair_mac<true>(tid, w, [=](int off, u64 x, u64 y) { st2(w_peer + off, x, y); }, key, corr2, rank, par);
             cluster_barrier();
         }
-        if (tid >= PAIR_INV_WORKERS) {
-            if (i + 1 < p.n) {
-                stage_key(i + 1, tid - PAIR_INV_WORKERS, PAIR_THREADS - PAIR_INV_WORKERS);
-                cp_async_wait<0>();                            // landed before this thread reaches the barrier that ends the step
-            }
-        } else {
-            auto sync_workers = [] { asm volatile("bar.sync 1, %0;" ::"n"(PAIR_INV_WORKERS) : "memory"); };
-            if (ASYNC) mbar_wait(bar0 + 8 * par, (unsigned)(i >> 1) & 1u);   // the peer's partial sums have landed
-            pair_inv3_a(tid, w, par);
-            sync_workers();
-            pair_inv3_b(tid, w, par);
-            sync_workers();
-            pair_inv2(tid, w, par);
-            sync_workers();
-            pair_inv1_a(tid, w, twd_inv, par);
-            sync_workers();
-            pair_inv1_b(tid, acc, w, par);
-        }
+        if (ASYNC) mbar_wait(bar0 + 8 * par, (unsigned)(i >> 1) & 1u);       // the peer's partial sums have landed
+        pair_inv3_a(tid, w, par);
+        __syncthreads();
+        pair_inv3_b(tid, w, par);
+        __syncthreads();
+        if (tid < PAIR_INV_WORKERS) pair_inv2(tid, w, par);
+        else if (i + 1 < p.n) stage_key(i + 1, tid - PAIR_INV_WORKERS, PAIR_THREADS - PAIR_INV_WORKERS);
+        __syncthreads();
+        pair_inv1_a(tid, w, twd_inv, par);
+        __syncthreads();
+        pair_inv1_b(tid, acc, w, par);
+        cp_async_wait<0>();                                    // the staged key row, before the barrier that ends the step
         if (tid == 0) rot[par ^ 1] = next;
         __syncthreads();
     }

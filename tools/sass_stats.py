@@ -108,6 +108,21 @@ def main():
             if line.startswith('}'):
                 in_step = False
     step_call_lines = [i for i, l in enumerate(ksrc, 1) if 'br2_step<true' in l and 'void' not in l]
+    if 'pair' in args.kernel:
+        # the pair shape (blind_rotate_pair_kernel): phases are the pair_* calls of its step loop.  Each pair_* wrapper
+        # holds BOTH thread halves (`if (h) f<1>(...) else f<0>(...)`), so a thread executes about half of the static
+        # count of a split phase; the MAC loops run twice (two rows per thread).
+        phase_lines, in_kernel_src = {}, False
+        for i, line in enumerate(ksrc, 1):
+            if 'blind_rotate_pair_kernel(' in line:
+                in_kernel_src = True
+            if in_kernel_src:
+                m = re.search(r'\b(pair_[a-z0-9_]+)(?:<[a-z]+>)?\(', line)
+                if m:
+                    phase_lines[i] = 'phase_' + m.group(1)
+                if line.startswith('}'):
+                    in_kernel_src = False
+        step_call_lines = list(phase_lines)
 
     # lines of br_phases.cuh inside a `switch (g)` (warp-uniform 4-way): each branch runs for a quarter of the warps
     bpath = os.path.join(ROOT, 'nufhe_b200', 'csrc', 'br_phases.cuh')
