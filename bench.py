@@ -17,7 +17,7 @@ torchrun (configs[4]: 65536 ciphertexts over 8 GPUs).  n=500, N=1024, k=1, l=2, 
                  the build x the work of the launch, against SMs x 4 schedulers x the SM clock sampled in the run)
   mux, ntt       the other two legs of BASELINE.json's metric, measured in the same process (N = 1 only):
                  gate_mux at the same batch, and the stand-alone transform in GB/s against the HBM peak
-  batch_sweep    gate_nand at {1, 64, 256, 1024, 4096, 16384, 65536} ciphertexts on one GPU (BASELINE.json configs[3])
+  batch_sweep    gate_nand at {1, 16, 64, 256, 1024, 4096, 16384, 65536} ciphertexts on one GPU (BASELINE.json configs[3])
   per_gpu_batch_sweep   ms/gate at {256, 4096, 8192} ciphertexts per GPU (multi-GPU runs)
   parity_checked        the first outputs of the timed gate on EVERY rank against the CPU oracle, in the run
   cpu_baseline   the CPU port of the reference algorithm (oracle/, C + OpenMP) on a bounded sample, all host cores;
@@ -430,7 +430,7 @@ def run_b200_arm(args):
             extras['ntt'] = measure_ntt(thr, args.ntt_transforms, flush_buf, measured_peak_hbm()[0])
             # BASELINE.json configs[3]: batch sweep of gate_nand on one GPU (device-resident operands, L2 flushed)
             sweep = []
-            for b in (1, 64, 256, 1024, 4096, 16384, 65536):
+            for b in (1, 16, 64, 256, 1024, 4096, 16384, 65536):
                 r = measure_case(make_case(b, 'nand', 77), 3 if b <= 4096 else 2, 3, with_e2e=False)
                 sweep.append({'batch': b, 'ms_per_step': r['ms_per_step'], 'ms_per_gate': r['ms_per_gate'],
                               'gates_per_s': r['gates_per_s'],
