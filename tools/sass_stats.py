@@ -128,6 +128,19 @@ def main():
     bpath = os.path.join(ROOT, 'nufhe_b200', 'csrc', 'br_phases.cuh')
     case_lines = {i for i, l in enumerate(open(bpath).read().splitlines(), 1) if re.match(r'\s*(case \d+|default):', l)}
 
+    # lines of br_phases.cuh inside the digit loop of phase_fwd1_both_digits (a real loop, two iterations per step)
+    twice_lines = set()
+    bsrc0 = open(bpath).read().splitlines()
+    for i, l in enumerate(bsrc0, 1):
+        if 'for (int j = 0; j < 2; j++)' in l:
+            depth, j = 0, i
+            while True:
+                depth += bsrc0[j - 1].count('{') - bsrc0[j - 1].count('}')
+                twice_lines.add(j)
+                if depth <= 0 and j > i:
+                    break
+                j += 1
+
     # lines of br_phases.cuh inside an `if (canon_needed(...)) { ... }` block: the rare path of the deferred
     # canonicalisation (taken with probability ~2^-28 per task) -- not part of the executed step
     rare_lines = set()
@@ -191,6 +204,8 @@ def main():
         if phase != 'other' and not in_loop:
             phase = 'plain:' + phase     # the non-rotating instantiation (nb_external_product)
         w = 0.25 if any(path.endswith('br_phases.cuh') and line in case_lines for path, line in chain) else 1
+        if any(path.endswith('br_phases.cuh') and line in twice_lines for path, line in chain):
+            w *= 2
         if any(path.endswith('br_phases.cuh') and line in rare_lines for path, line in chain):
             counts['rare:' + phase][pipe] += w
             continue
