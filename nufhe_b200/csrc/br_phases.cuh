@@ -34,6 +34,9 @@ namespace nb {
 #ifndef NB_BR_STAGE_KEY
 #define NB_BR_STAGE_KEY 0
 #endif
+#ifndef NB_FWD1_BOTH_DIGITS
+#define NB_FWD1_BOTH_DIGITS 1
+#endif
 // Deferred canonicalisation: the general multiplications of fwd1 / inv1 and the MAC leave their result as "some
 // 64-bit value of the right residue" (ff_mul_nc, ff_dot4_sub_nc) instead of paying 6 ALU instructions per element
 // for the conditional subtraction of p.  Such a value is above p with probability 2^-32 (a few elements per
@@ -125,6 +128,9 @@ template <int CT_, int THREADS_, int CTAS_ = 512 / THREADS_, bool TWD_GLOBAL_ = 
     // 16-element forward task, 8 outputs each (split forward phases below)
     static constexpr bool SPLIT_FWD = THREADS == 512 * CT;
     static constexpr int FWD_SWEEPS = SPLIT_FWD ? 1 : 256 * CT / THREADS;      // sweeps of the forward phases
+    // two forward tasks per thread: the first pass takes both digit polynomials of one accumulator polynomial at once
+    // and shares the rotation between them (phase_fwd1_both_digits)
+    static constexpr bool FWD1_BOTH_DIGITS = NB_FWD1_BOTH_DIGITS && !SPLIT_FWD && FWD_SWEEPS == 2;
     static constexpr int INV_TASKS = 128 * CT;                 // threads with work in the inverse phases
     // Twice as many threads as inverse tasks (the wide shape): every inverse task is shared by two threads of
     // different warps, 8 elements each ("split inverse phases" below) instead of leaving half of the warps idle
@@ -302,6 +308,44 @@ NB_HD void phase_fwd1(int task, const i32 *acc_all, u64 *w_all, const u64 *twd, 
     run_network<NetDif16>(v, load);
     u64 *w = w_all + p * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
     store_twiddled(v, w, twd + j2);
+}
+
+// The same pass for BOTH digit polynomials of one accumulator polynomial: task = (pm = ct * 2 + mi, j2).  The rotated
+// coefficients (two loads, a select and a subtraction each) and the decomposition offset are computed once and serve both
+// digits; the digit loop is a real loop (run-time shift amount), so the code is no longer than one digit's.
+// Used when a thread would otherwise run two tasks of this pass (BrCfg: FWD1_BOTH_DIGITS).
+template <bool ROTATE>
+NB_HD void phase_fwd1_both_digits(int task, const i32 *acc_all, u64 *w_all, const u64 *twd, const int *rot_a)
+{
+    const int j2 = task & 63, pm = task >> 6;
+    const i32 *acc = acc_all + pm * NTT_N;
+    const int a = ROTATE ? rot_a[pm >> 1] : 0;
+    const int ar = a & (NTT_N - 1);
+    const bool flip = (a >> 10) & 1;
+    u32 t[16];                                         // coefficient + decomposition offset (decomp_udigit)
+    static_for<0, 16>([&](auto J) {
+        constexpr int j1 = decltype(J)::value;
+        const int idx = 64 * j1 + j2;
+        const i32 c = ROTATE ? rotate_minus_one(acc, idx, ar, flip) : acc[idx];
+        t[j1] = (u32)c + (0x80000000u + (1u << 21));
+    });
+    u64 *w = w_all + pm * 2 * POLY_STRIDE + col_of(j2 >> 4, j2 & 15);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < 2; j++) {
+        const int sh = 22 - 10 * j;
+        u64 v[16];
+        auto load = [&]() {
+            static_for<0, 16>([&](auto J) {
+                constexpr int j1 = decltype(J)::value;
+                v[j1] = ff_twist_small<j1>((t[j1] >> sh) & 1023u);
+            });
+        };
+        load();
+        run_network<NetDif16>(v, load);
+        store_twiddled(v, w + j * POLY_STRIDE, twd + j2);
+    }
 }
 
 // ---- fwd2 / inv2: task = (poly p, row, g); 16 elements (a, e), b = 4 g + e ---------------------------

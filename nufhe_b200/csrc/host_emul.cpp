@@ -116,11 +116,18 @@ template <class Cfg> static void phase_step(i32 *acc_io, const u64 *bk_ref_row, 
             });
         }
     } else {
-        for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
+        if constexpr (Cfg::FWD1_BOTH_DIGITS) {
             for (int tid = 0; tid < TH; tid++) {
-                if (rot) phase_fwd1<true>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
-                else phase_fwd1<false>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
+                if (rot) phase_fwd1_both_digits<true>(tid, acc.data(), w.data(), T.fwd.data(), rots);
+                else phase_fwd1_both_digits<false>(tid, acc.data(), w.data(), T.fwd.data(), rots);
             }
+        } else {
+            for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
+                for (int tid = 0; tid < TH; tid++) {
+                    if (rot) phase_fwd1<true>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
+                    else phase_fwd1<false>(it * TH + tid, acc.data(), w.data(), T.fwd.data(), rots);
+                }
+        }
         for (int it = 0; it < Cfg::FWD_SWEEPS; it++)
             for (int tid = 0; tid < TH; tid++) { int p, r, g; map_fwd2<Cfg>(tid, it, p, r, g); phase_fwd2(p, r, g, w.data()); }
         for (int it = 0; it < Cfg::FWD_SWEEPS; it++)

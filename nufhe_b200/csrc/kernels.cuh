@@ -387,8 +387,12 @@ NB_D void br2_step(const Br2Smem &s, const u64 *__restrict__ bk_row, const int *
         }
         __syncthreads();
     } else {
+        if constexpr (Cfg::FWD1_BOTH_DIGITS) {
+            phase_fwd1_both_digits<ROTATE>(tid, s.acc, s.w, s.twd_fwd, rot);
+        } else {
 #pragma unroll 1
-        for (int it = 0; it < Cfg::FWD_SWEEPS; it++) phase_fwd1<ROTATE>(it * Cfg::THREADS + tid, s.acc, s.w, s.twd_fwd, rot);
+            for (int it = 0; it < Cfg::FWD_SWEEPS; it++) phase_fwd1<ROTATE>(it * Cfg::THREADS + tid, s.acc, s.w, s.twd_fwd, rot);
+        }
         __syncthreads();
 #pragma unroll 1
         for (int it = 0; it < Cfg::FWD_SWEEPS; it++) { int p, r, g; map_fwd2<Cfg>(tid, it, p, r, g); phase_fwd2(p, r, g, s.w); }
