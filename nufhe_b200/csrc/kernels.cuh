@@ -4,6 +4,8 @@
 // polynomials live in shared memory; every CMux step is seven CTA-wide phases (br_phases.cuh) separated by
 // __syncthreads, 16 field elements per thread and phase.  The kernel is persistent: at most one wave of CTAs, which
 // pull (chain, chunk) work items from a FIFO of ready chains in global memory, so that any batch is spread over all SMs.
+// The smallest batches take a second kernel that spreads ONE ciphertext over a cluster of two SMs (pair shape: the step
+// divides along the two accumulator polynomials, one 8 KB exchange per step through distributed shared memory).
 // The stand-alone transforms reuse the same phases behind cp.async-staged, 128-bit input / output.  The key switch is a
 // TMA-fed producer / consumer pipeline.  Then the separate steps of the reference's multi-kernel bootstrap, and the
 // key-generation kernels (LWE dot product, key-switch key).
@@ -585,8 +587,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::CTAS_PER_SM) blind_rotate_k
 }
 
 // ---- pair shape: one ciphertext per cluster of two CTAs (br_phases.cuh: "pair shape") -------------------------------
-// Lowest latency for batches of at most half the SM count.  No work queue (one cluster per ciphertext, one wave or
-// plain hardware queueing of clusters), blind rotation only (`plain` external products take the single-CTA shapes).
+// Lowest latency for batches up to 3/8 of the SM count (capi.cu: pair_max).  No work queue (one cluster per ciphertext,
+// one wave or plain hardware queueing of clusters), blind rotation only (`plain` external products take the single-CTA shapes).
 // Dynamic shared memory is requested well above what the shape needs so that the two CTAs of a cluster can never
 // share an SM.
 constexpr size_t BR_PAIR_SMEM_USED = (size_t)PAIR_POLYS * POLY_STRIDE * sizeof(u64) + 2 * NTT_N * sizeof(u64) + NTT_N * sizeof(i32) + 64 +

@@ -254,6 +254,32 @@ def test_mul_and_dot4():
         assert in_range(got) and got % P == sum(x * y for x, y in zip(a, b)) % P
 
 
+def ff_dotn_sub_nc(a, b, c):
+    """ff_dot4_sub_nc / ff_dot2_sub_nc (the MAC of the fused bootstrap, 4 terms; the pair shape's, 2 terms)."""
+    acc = list(mul128(a[0], b[0])) + [0]
+    for k in range(1, len(a)):
+        e = run('mac128', a=a[k], b=b[k], c0=acc[0], c1=acc[1], c2=acc[2], c3=acc[3], c4=acc[4])
+        acc = [e['c%d' % i] for i in range(5)]
+    return ff_sub(ff_sub(ff_reduce_limbs_nc(*acc[:4]), (acc[4] << 32) & M64), c)
+
+
+def test_dot_products_minus_correction_keep_the_residue():
+    """The not-canonicalised MAC results: right residue, and a value above p always shows a high limb of 2^32 - 1 --
+    the trigger of the rare-path fix-up (br_phases.cuh: canon_needed)."""
+    for n in (2, 4):
+        cases = [([P] * n, [P] * n, 0), ([P - 1] * n, [P - 1] * n, P), ([P] * n, [1] * n, P - 1)]
+        for _ in range(400):
+            a, b = rand_field(n), rand_field(n)
+            if RNG.random() < 0.3:
+                a[RNG.randrange(n)] = RNG.choice(EDGE64) % (P + 1)
+                b[RNG.randrange(n)] = RNG.choice(EDGE64) % (P + 1)
+            cases.append((a, b, RNG.choice([0, 1, P - 1, P, RNG.randrange(P)])))
+        for a, b, c in cases:
+            got = ff_dotn_sub_nc(a, b, c)
+            assert 0 <= got < (1 << 64) and got % P == (sum(x * y for x, y in zip(a, b)) - c) % P
+            assert got <= P or (got >> 32) == M32
+
+
 def test_limb_combinations_on_edge_limbs():
     phi = 1 << 32
     ys2 = [0, 1, 2, (1 << 30), (1 << 31) - 2, (1 << 31) - 1]          # y2 < 2^31 by construction (r <= 31)
