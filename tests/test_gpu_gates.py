@@ -118,25 +118,28 @@ def test_full_size_batches_decrypt_to_truth_table(eng, keys, dev_keys, batch):
 
 
 def test_all_cta_shapes_give_the_same_bits(keys, monkeypatch):
-    """The fused kernel has four shapes: 2 ciphertexts per 256 threads (throughput), 1 ciphertext per 256 threads
+    """The fused bootstrap has four shapes: 2 ciphertexts per 256 threads (throughput), 1 ciphertext per 256 threads
     (inverse phases split over thread pairs), 1 ciphertext per 512 threads (forward phases split as well; batches
     up to 1.5 ciphertexts per SM) and 1 ciphertext per cluster of two 256-thread CTAs on two SMs (partial sums of the
-    MAC exchanged through distributed shared memory; batches up to half the SM count).  Force each shape for the same
+    MAC exchanged through distributed shared memory, in both exchange variants; batches up to 3/8 of the SM count).  Force
+    each shape for the same
     inputs, including a ragged batch and one larger than a wave (time-sliced, or clusters queued by the hardware); all
     must equal the oracle and each other."""
     from nufhe_b200.engine import Engine
     rng = G.rs(480)
-    shapes = {'default': ('0', '0', '0'), 'wide': ('1000000', '0', '0'), 'wide2': ('1000000', '1000000', '0'),
-              'pair': ('0', '0', '1000000')}
+    shapes = {'default': ('0', '0', '0', '1'), 'wide': ('1000000', '0', '0', '1'), 'wide2': ('1000000', '1000000', '0', '1'),
+              'pair': ('0', '0', '1000000', '1'),            # exchange by st.async + mbarrier (the default)
+              'pair_barrier': ('0', '0', '1000000', '0')}    # exchange by plain remote stores + barrier.cluster
     for B in (1, 5, 301):
         bits_a, bits_b = rng.randint(0, 2, B).astype(bool), rng.randint(0, 2, B).astype(bool)
         a, b = keys.encrypt(bits_a), keys.encrypt(bits_b)
         want = O.gate_binary('nand', a, b, keys.bk, keys.ks) if B <= 5 else None
         outs = {}
-        for name, (wide_max, wide2_max, pair_max) in shapes.items():
+        for name, (wide_max, wide2_max, pair_max, pair_async) in shapes.items():
             monkeypatch.setenv('NUFHE_B200_WIDE_MAX', wide_max)
             monkeypatch.setenv('NUFHE_B200_WIDE2_MAX', wide2_max)
             monkeypatch.setenv('NUFHE_B200_PAIR_MAX', pair_max)
+            monkeypatch.setenv('NUFHE_B200_PAIR_ASYNC', pair_async)
             eng = Engine()
             dk = (eng.bk_prepare(eng.to_device(keys.bk)),
                   (eng.to_device(keys.ks_a), eng.to_device(keys.ks_b), eng.to_device(keys.ks_cv)))
@@ -145,7 +148,7 @@ def test_all_cta_shapes_give_the_same_bits(keys, monkeypatch):
             if want is not None:
                 assert (out[0] == want[0]).all() and (out[1] == want[1]).all(), (B, name)
             assert (keys.decrypt(out) == ~(bits_a & bits_b)).all()
-        for name in ('wide', 'wide2', 'pair'):
+        for name in ('wide', 'wide2', 'pair', 'pair_barrier'):
             for x, y in zip(outs['default'], outs[name]):
                 assert (x[0] == y[0]).all() and (x[1] == y[1]).all(), (B, name)
 
