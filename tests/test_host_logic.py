@@ -277,6 +277,25 @@ def test_pair_shape_steps_match_oracle(emul):
         assert (a == O.blind_rotate(acc, rows, r.reshape(1, -1))).all()
 
 
+def test_committed_traffic_capture_belongs_to_the_built_kernel():
+    """bench.py quotes `roofline.traffic` from profiles/r2_traffic.json only when the kernel of the running library has
+    the same static per-phase instruction counts as the one the ncu capture was taken on (tools/sass_stats.py, no GPU
+    needed).  Guard against kernel edits that forget to re-capture: the committed fingerprint must match this build."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+    if not (shutil.which('cuobjdump') and shutil.which('nvdisasm')):
+        pytest.skip('CUDA binary utilities not on PATH')
+    with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as f:
+        fp = json.load(f)['kernel_fingerprint']
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'sass_stats.py'), '--json'], capture_output=True,
+                       text=True, timeout=300)
+    cur = json.loads(r.stdout)
+    assert cur['phases'] == fp['phases'] and cur['per_thread_step_total'] == fp['per_thread_step_total']
+    assert cur['per_thread_step_total'] > 5000          # the tool found the step loop
+
+
 def test_uint_bit_helpers_roundtrip():
     from nufhe_b200.operators_integer import uintarray_to_bitarray, bitarray_to_uintarray
     xs = numpy.array([[0, 1, 255], [128, 77, 200]], numpy.uint8)
